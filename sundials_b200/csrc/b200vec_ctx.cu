@@ -1,0 +1,347 @@
+/* b200vec_ctx.cu -- execution context, workspace, memory and error plumbing
+ * of the B200-native N_Vector kernel library (C ABI in include/b200vec.h).
+ *
+ * Replaces, for this vector, what the reference spreads over
+ *   - SUNCudaExecPolicy objects      (include/sundials/sundials_cuda_policies.hpp:71-235)
+ *   - per-vector reduction / fused scratch (src/nvector/cuda/nvector_cuda.cu:2277-2630)
+ *   - SUNMemoryHelper_Cuda           (src/sunmemory/cuda/sundials_cuda_memory.cu:131-351)
+ * with ONE workspace per context that every clone shares.
+ */
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "b200vec_internal.h"
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  if (getenv("B200VEC_VERBOSE")) fprintf(stderr, "[b200vec] error %d: %s\n", code, g_err);
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what)
+{
+  if (e == cudaSuccess) return B200VEC_OK;
+  int code = (e == cudaErrorMemoryAllocation) ? B200VEC_ERR_NOMEM
+             : (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? B200VEC_ERR_NODEVICE
+                                                                            : B200VEC_ERR_CUDA;
+  return set_error(code, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+int check_launch(b200vec_ctx ctx, const char* kernel)
+{
+  if (ctx->tune.count_launches) ctx->launches++;
+  return check_cuda(cudaGetLastError(), kernel);
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char* b200vec_last_error(void) { return g_err; }
+const char* b200vec_version(void) { return "b200vec 0.1 (sm_100a, fp64, -fmad=false)"; }
+
+int b200vec_ctx_create(b200vec_ctx* out, int device, void* stream)
+{
+  if (!out) return set_error(B200VEC_ERR_ARG, "ctx_create: NULL out");
+  *out    = nullptr;
+  int ndev = 0;
+  int rc   = check_cuda(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount");
+  if (rc) return rc;
+  if (ndev < 1) return set_error(B200VEC_ERR_NODEVICE, "no CUDA device visible");
+  if (device < 0)
+  {
+    rc = check_cuda(cudaGetDevice(&device), "cudaGetDevice");
+    if (rc) return rc;
+  }
+  if (device >= ndev) return set_error(B200VEC_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+
+  b200vec_ctx c = new (std::nothrow) b200vec_ctx_s();
+  if (!c) return set_error(B200VEC_ERR_NOMEM, "ctx_create: host allocation failed");
+  c->device = device;
+  c->stream = (cudaStream_t)stream;
+  DeviceGuard g(device);
+
+  rc = check_cuda(cudaMalloc((void**)&c->d_partials, sizeof(double) * kMaxOut * kMaxPartialBlocks),
+                  "cudaMalloc(partials)");
+  if (!rc) rc = check_cuda(cudaMalloc((void**)&c->d_count, sizeof(unsigned int) * kMaxRows), "cudaMalloc(count)");
+  if (!rc) rc = check_cuda(cudaMemset(c->d_count, 0, sizeof(unsigned int) * kMaxRows), "cudaMemset(count)");
+  if (!rc) rc = check_cuda(cudaMalloc((void**)&c->d_result, sizeof(double) * kMaxRows), "cudaMalloc(result)");
+  if (!rc) rc = check_cuda(cudaMemset(c->d_result, 0, sizeof(double) * kMaxRows), "cudaMemset(result)");
+  if (!rc)
+    rc = check_cuda(cudaHostAlloc((void**)&c->h_result, sizeof(double) * kMaxRows, cudaHostAllocMapped),
+                    "cudaHostAlloc(result)");
+  if (!rc)
+    rc = check_cuda(cudaHostGetDevicePointer((void**)&c->h_result_dev, c->h_result, 0),
+                    "cudaHostGetDevicePointer(result)");
+  if (rc)
+  {
+    b200vec_ctx_release(c);
+    return rc;
+  }
+  memset(c->h_result, 0, sizeof(double) * kMaxRows);
+  *out = c;
+  return B200VEC_OK;
+}
+
+int b200vec_ctx_retain(b200vec_ctx ctx)
+{
+  B200_CHECK_CTX(ctx);
+  ctx->refcount++;
+  return B200VEC_OK;
+}
+
+int b200vec_ctx_release(b200vec_ctx ctx)
+{
+  B200_CHECK_CTX(ctx);
+  if (--ctx->refcount > 0) return B200VEC_OK;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->nccl_comm) b200vec_comm_finalize(ctx);
+  for (auto& kv : ctx->cache) cudaFree(kv.second);
+  ctx->cache.clear();
+  if (ctx->d_partials) cudaFree(ctx->d_partials);
+  if (ctx->d_count) cudaFree(ctx->d_count);
+  if (ctx->d_result) cudaFree(ctx->d_result);
+  if (ctx->d_commbuf) cudaFree(ctx->d_commbuf);
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  delete ctx;
+  return B200VEC_OK;
+}
+
+static std::mutex g_default_mu;
+static std::map<int, b200vec_ctx> g_default;
+
+int b200vec_ctx_default(b200vec_ctx* out)
+{
+  if (!out) return set_error(B200VEC_ERR_ARG, "ctx_default: NULL out");
+  int dev = 0;
+  int rc  = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g_default_mu);
+  auto it = g_default.find(dev);
+  if (it == g_default.end())
+  {
+    b200vec_ctx c = nullptr;
+    rc            = b200vec_ctx_create(&c, dev, nullptr);
+    if (rc) return rc;
+    it = g_default.emplace(dev, c).first; /* lives for the whole process */
+  }
+  *out = it->second;
+  return B200VEC_OK;
+}
+
+int b200vec_ctx_set_stream(b200vec_ctx ctx, void* stream)
+{
+  B200_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  /* pending work on the old stream must finish before results on the new one
+     can depend on it */
+  int rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  ctx->stream = (cudaStream_t)stream;
+  return rc;
+}
+
+void* b200vec_ctx_get_stream(b200vec_ctx ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int b200vec_ctx_device(b200vec_ctx ctx) { return ctx ? ctx->device : -1; }
+
+int b200vec_ctx_sync(b200vec_ctx ctx)
+{
+  B200_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  return check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+}
+
+int b200vec_ctx_set_tuning(b200vec_ctx ctx, const char* key, int64_t value)
+{
+  B200_CHECK_CTX(ctx);
+  if (!key) return set_error(B200VEC_ERR_ARG, "set_tuning: NULL key");
+  if (!strcmp(key, "max_blocks"))
+  {
+    if (value < 1 || value > kMaxPartialBlocks)
+      return set_error(B200VEC_ERR_ARG, "max_blocks must be in [1,%d]", kMaxPartialBlocks);
+    ctx->tune.max_blocks = value;
+  }
+  else if (!strcmp(key, "vec_width"))
+  {
+    if (value != 0 && value != 1 && value != 2 && value != 4)
+      return set_error(B200VEC_ERR_ARG, "vec_width must be 0,1,2 or 4");
+    ctx->tune.vec_width = value;
+  }
+  else if (!strcmp(key, "unroll"))
+  {
+    if (value != 0 && value != 1 && value != 2 && value != 4)
+      return set_error(B200VEC_ERR_ARG, "unroll must be 0,1,2 or 4");
+    ctx->tune.unroll = value;
+  }
+  else if (!strcmp(key, "exact_threshold"))
+  {
+    if (value < 0 || value > kExactMaxElems)
+      return set_error(B200VEC_ERR_ARG, "exact_threshold must be in [0,%d]", kExactMaxElems);
+    ctx->tune.exact_threshold = value;
+  }
+  else if (!strcmp(key, "count_launches"))
+  {
+    ctx->tune.count_launches = value ? 1 : 0;
+    ctx->launches            = 0;
+  }
+  else return set_error(B200VEC_ERR_ARG, "unknown tuning key '%s'", key);
+  return B200VEC_OK;
+}
+
+int64_t b200vec_ctx_get_tuning(b200vec_ctx ctx, const char* key)
+{
+  if (!ctx || !key) return -1;
+  if (!strcmp(key, "max_blocks")) return ctx->tune.max_blocks;
+  if (!strcmp(key, "vec_width")) return ctx->tune.vec_width;
+  if (!strcmp(key, "unroll")) return ctx->tune.unroll;
+  if (!strcmp(key, "exact_threshold")) return ctx->tune.exact_threshold;
+  if (!strcmp(key, "count_launches")) return ctx->tune.count_launches;
+  return -1;
+}
+
+int64_t b200vec_ctx_launch_count(b200vec_ctx ctx) { return ctx ? ctx->launches : -1; }
+
+/* ---------------------------------------------------------------- memory */
+
+int b200vec_malloc_device(b200vec_ctx ctx, size_t bytes, void** ptr)
+{
+  B200_CHECK_CTX(ctx);
+  if (!ptr) return set_error(B200VEC_ERR_ARG, "malloc_device: NULL ptr");
+  *ptr = nullptr;
+  if (bytes == 0) return B200VEC_OK;
+  auto it = ctx->cache.find(bytes);
+  if (it != ctx->cache.end())
+  {
+    *ptr = it->second;
+    ctx->cache.erase(it);
+    ctx->cached_bytes -= bytes;
+    return B200VEC_OK;
+  }
+  DeviceGuard g(ctx->device);
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e == cudaErrorMemoryAllocation && !ctx->cache.empty())
+  {
+    /* give cached blocks back to the driver and retry once */
+    (void)cudaGetLastError();
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->cache) cudaFree(kv.second);
+    ctx->cache.clear();
+    ctx->cached_bytes = 0;
+    e                 = cudaMalloc(ptr, bytes);
+  }
+  return check_cuda(e, "cudaMalloc");
+}
+
+int b200vec_free_device(b200vec_ctx ctx, void* ptr, size_t bytes)
+{
+  B200_CHECK_CTX(ctx);
+  if (!ptr) return B200VEC_OK;
+  /* stream-ordered reuse is safe: every consumer of a cached block is enqueued
+     on the same ctx stream after all earlier users */
+  if (bytes > 0 && ctx->cached_bytes + bytes <= ctx->cache_limit)
+  {
+    ctx->cache.emplace(bytes, ptr);
+    ctx->cached_bytes += bytes;
+    return B200VEC_OK;
+  }
+  DeviceGuard g(ctx->device);
+  return check_cuda(cudaFree(ptr), "cudaFree");
+}
+
+int b200vec_malloc_host(b200vec_ctx ctx, size_t bytes, void** ptr)
+{
+  B200_CHECK_CTX(ctx);
+  if (!ptr) return set_error(B200VEC_ERR_ARG, "malloc_host: NULL ptr");
+  *ptr = nullptr;
+  if (bytes == 0) return B200VEC_OK;
+  DeviceGuard g(ctx->device);
+  return check_cuda(cudaHostAlloc(ptr, bytes, cudaHostAllocMapped | cudaHostAllocPortable), "cudaHostAlloc");
+}
+
+int b200vec_free_host(b200vec_ctx ctx, void* ptr)
+{
+  B200_CHECK_CTX(ctx);
+  if (!ptr) return B200VEC_OK;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  return check_cuda(cudaFreeHost(ptr), "cudaFreeHost");
+}
+
+int b200vec_malloc_managed(b200vec_ctx ctx, size_t bytes, void** ptr)
+{
+  B200_CHECK_CTX(ctx);
+  if (!ptr) return set_error(B200VEC_ERR_ARG, "malloc_managed: NULL ptr");
+  *ptr = nullptr;
+  if (bytes == 0) return B200VEC_OK;
+  DeviceGuard g(ctx->device);
+  return check_cuda(cudaMallocManaged(ptr, bytes, cudaMemAttachGlobal), "cudaMallocManaged");
+}
+
+int b200vec_free_managed(b200vec_ctx ctx, void* ptr)
+{
+  B200_CHECK_CTX(ctx);
+  if (!ptr) return B200VEC_OK;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  return check_cuda(cudaFree(ptr), "cudaFree(managed)");
+}
+
+int b200vec_copy_h2d(b200vec_ctx ctx, void* dst, const void* src, size_t bytes, int sync)
+{
+  B200_CHECK_CTX(ctx);
+  if (bytes == 0) return B200VEC_OK;
+  DeviceGuard g(ctx->device);
+  int rc = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(H2D)");
+  if (!rc && sync) rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  return rc;
+}
+
+int b200vec_copy_d2h(b200vec_ctx ctx, void* dst, const void* src, size_t bytes, int sync)
+{
+  B200_CHECK_CTX(ctx);
+  if (bytes == 0) return B200VEC_OK;
+  DeviceGuard g(ctx->device);
+  int rc = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync(D2H)");
+  if (!rc && sync) rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  return rc;
+}
+
+int b200vec_copy_d2d(b200vec_ctx ctx, void* dst, const void* src, size_t bytes)
+{
+  B200_CHECK_CTX(ctx);
+  if (bytes == 0) return B200VEC_OK;
+  DeviceGuard g(ctx->device);
+  return check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream), "cudaMemcpyAsync(D2D)");
+}
+
+double* b200vec_result_device(b200vec_ctx ctx) { return ctx ? ctx->d_result : nullptr; }
+
+int b200vec_result_fetch(b200vec_ctx ctx, int count, double* result_host)
+{
+  B200_CHECK_CTX(ctx);
+  if (count < 0 || count > kMaxRows || !result_host) return set_error(B200VEC_ERR_ARG, "result_fetch: bad count/ptr");
+  DeviceGuard g(ctx->device);
+  /* after an allreduce the pinned slots are stale: copy from the device slots */
+  int rc = check_cuda(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(double) * count, cudaMemcpyDeviceToHost,
+                                      ctx->stream),
+                      "cudaMemcpyAsync(result)");
+  if (!rc) rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  if (!rc)
+    for (int i = 0; i < count; i++) result_host[i] = ctx->h_result[i];
+  return rc;
+}
+
+} /* extern "C" */

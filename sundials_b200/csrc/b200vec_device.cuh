@@ -1,0 +1,117 @@
+/* b200vec_device.cuh -- device-side building blocks for the sm_100a kernels.
+ *
+ *  - wide global loads/stores: 256-bit (LDG.E.256 / STG.E.256, new on sm_100),
+ *    128-bit and 64-bit, all with L1::no_allocate (streaming data has no reuse
+ *    inside a kernel; default L2 policy is kept on purpose -- inside an integrator
+ *    the output of one op is the input of the next and the 126 MB L2 holds it).
+ *  - deterministic warp / block combiners for the two-stage reductions.
+ */
+#ifndef B200VEC_DEVICE_CUH
+#define B200VEC_DEVICE_CUH
+
+#include <cfloat>
+#include <cstdint>
+
+#include "b200vec_internal.h"
+
+namespace b200 {
+
+/* ---- W-wide loads and stores (W doubles = 8W bytes, address 8W-aligned) ---- */
+template <int W>
+__device__ __forceinline__ void ldg(const double* p, double (&v)[W]);
+template <int W>
+__device__ __forceinline__ void stg(double* p, const double (&v)[W]);
+
+template <>
+__device__ __forceinline__ void ldg<1>(const double* p, double (&v)[1])
+{
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v[0]) : "l"(p) : "memory");
+}
+template <>
+__device__ __forceinline__ void ldg<2>(const double* p, double (&v)[2])
+{
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+               : "=d"(v[0]), "=d"(v[1])
+               : "l"(p)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void ldg<4>(const double* p, double (&v)[4])
+{
+  asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+               : "l"(p)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void stg<1>(double* p, const double (&v)[1])
+{
+  asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v[0]) : "memory");
+}
+template <>
+__device__ __forceinline__ void stg<2>(double* p, const double (&v)[2])
+{
+  asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+}
+template <>
+__device__ __forceinline__ void stg<4>(double* p, const double (&v)[4])
+{
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]),
+               "d"(v[3])
+               : "memory");
+}
+
+/* ---- combiners.  The predicates mirror nvector_serial.c:635,719 (strict
+ * comparisons, so NaNs never win) rather than fmax/fmin. ---- */
+struct CombSum
+{
+  static __device__ __forceinline__ double identity() { return 0.0; }
+  static __device__ __forceinline__ double apply(double a, double b) { return a + b; }
+  static constexpr bool order_sensitive = true;
+};
+struct CombMax
+{
+  static __device__ __forceinline__ double identity() { return 0.0; } /* max |x| starts at 0 (serial:627) */
+  static __device__ __forceinline__ double apply(double a, double b) { return (b > a) ? b : a; }
+  static constexpr bool order_sensitive = false;
+};
+struct CombMin
+{
+  static __device__ __forceinline__ double identity() { return DBL_MAX; }
+  static __device__ __forceinline__ double apply(double a, double b) { return (b < a) ? b : a; }
+  static constexpr bool order_sensitive = false;
+};
+
+template <class C>
+__device__ __forceinline__ double warp_combine(double v)
+{
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+  {
+    double o = __shfl_down_sync(0xffffffffu, v, off);
+    v        = C::apply(v, o);
+  }
+  return v; /* valid in lane 0 */
+}
+
+/* block-wide combine of one value per thread; result valid in thread 0.
+ * Fixed tree: lanes by shuffle, then the 8 warp leaders by shuffle in warp 0. */
+template <class C>
+__device__ __forceinline__ double block_combine(double v, double* smem /* >= kBlock/32 doubles */)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_combine<C>(v);
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  double r = C::identity();
+  if (warp == 0)
+  {
+    r = (lane < kBlock / 32) ? smem[lane] : C::identity();
+    r = warp_combine<C>(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+} // namespace b200
+#endif

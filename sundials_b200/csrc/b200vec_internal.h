@@ -1,0 +1,118 @@
+/* b200vec_internal.h -- host-side internals shared by the .cu translation units.
+ * Not installed; the public C ABI is include/b200vec.h. */
+#ifndef B200VEC_INTERNAL_H
+#define B200VEC_INTERNAL_H
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <vector>
+
+#include "b200vec.h"
+
+namespace b200 {
+
+constexpr int kBlock        = 256;  /* threads per CTA for every kernel               */
+constexpr int kSMs          = 148;  /* B200: 2 dies x 74 SMs                          */
+constexpr int kMaxBlocksDef = kSMs * 8; /* 8 x 256 threads = 2048 = full SM occupancy */
+constexpr int kMaxPartialBlocks = 4096; /* reduction partial rows (>= any max_blocks) */
+constexpr int kMaxOut       = 8;    /* outputs per multi-reduction launch             */
+constexpr int kMaxRows      = 64;   /* result slots per context                       */
+constexpr int kExactMaxElems = 4096; /* smem doubles available to the exact-order path */
+
+struct Tuning
+{
+  int64_t max_blocks      = kMaxBlocksDef;
+  int64_t vec_width       = 0; /* 0 = auto (widest the alignment allows) */
+  int64_t unroll          = 0; /* 0 = auto */
+  int64_t exact_threshold = 1024;
+  int64_t count_launches  = 0;
+};
+
+} // namespace b200
+
+struct NcclApi; /* b200vec_comm.cu */
+
+struct b200vec_ctx_s
+{
+  int device            = 0;
+  cudaStream_t stream   = nullptr;
+  int refcount          = 1;
+  b200::Tuning tune;
+  int64_t launches      = 0;
+
+  /* reduction workspace (device) */
+  double* d_partials    = nullptr; /* [kMaxOut][kMaxPartialBlocks]                 */
+  unsigned int* d_count = nullptr; /* [kMaxRows] last-block-done tickets, self-resetting */
+  double* d_result      = nullptr; /* [kMaxRows] result slots                       */
+  /* pinned + mapped host mirror of the result slots: the final pass of every
+     reduction kernel stores here directly, so a scalar-returning op costs one
+     stream sync and no memcpy */
+  double* h_result      = nullptr; /* host address   */
+  double* h_result_dev  = nullptr; /* device alias   */
+
+  /* exact-size free-list cache of device allocations (clone/destroy churn) */
+  std::multimap<size_t, void*> cache;
+  size_t cached_bytes = 0;
+  size_t cache_limit  = (size_t)8 << 30;
+
+  /* communicator (NULL = single rank) */
+  void* nccl_comm = nullptr;
+  int rank        = 0;
+  int nranks      = 1;
+  double* d_commbuf = nullptr;
+};
+
+namespace b200 {
+
+/* launch geometry shared by the streaming / reduction / fused launchers */
+struct MapCfg
+{
+  int W;    /* doubles per load/store: 4 = 256-bit, 2 = 128-bit, 1 = 64-bit */
+  int U;    /* independent wide loads in flight per operand and thread        */
+  int grid; /* CTAs                                                           */
+};
+MapCfg pick_map_cfg(b200vec_ctx ctx, int64_t n, int wmax);
+static inline int align_width(const void* p)
+{
+  if (!p) return 4; /* absent operand does not constrain */
+  uintptr_t a = (uintptr_t)p;
+  return (a % 32 == 0) ? 4 : (a % 16 == 0) ? 2 : 1;
+}
+int finish_reduction(b200vec_ctx ctx, int count, double* result_host);
+int linear_sum_dispatch(b200vec_ctx ctx, double a, const double* x, double b, const double* y, double* z,
+                        bool z_is_x, bool z_is_y, int64_t n);
+int scale_dispatch(b200vec_ctx ctx, double c, const double* x, double* z, int64_t n);
+
+int set_error(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+int check_launch(b200vec_ctx ctx, const char* kernel);
+
+/* RAII device guard so a context bound to device k works from any thread */
+struct DeviceGuard
+{
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev)
+  {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev)
+    {
+      cudaSetDevice(dev);
+      switched = true;
+    }
+  }
+  ~DeviceGuard()
+  {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+} // namespace b200
+
+#define B200_CHECK_CTX(ctx)                                                   \
+  do {                                                                        \
+    if ((ctx) == nullptr) return b200::set_error(B200VEC_ERR_ARG, "%s: NULL context", __func__); \
+  } while (0)
+
+#endif

@@ -1,0 +1,622 @@
+/* b200vec_reduce.cu -- local reduction kernels for sm_100a.
+ *
+ * Two-stage, single-launch, deterministic:
+ *   stage 1  every thread folds its grid-stride share sequentially into W
+ *            register accumulators (wide loads, U tiles in flight), folds those
+ *            in fixed order, then warp shuffle tree -> 8 warp leaders -> CTA value,
+ *            written to partials[blockIdx.x];
+ *   stage 2  the last CTA to finish (ticket counter) folds partials[0..grid) in
+ *            FIXED INDEX ORDER (thread t takes t, t+256, ...; then the same
+ *            tree), so the result does not depend on which CTA happened to be
+ *            last or on scheduling: run-to-run bitwise reproducible.  It stores
+ *            the value to the context's device result slot and to a pinned,
+ *            device-mapped host slot -- a scalar-returning N_Vector op then needs
+ *            one stream sync and no memcpy (the reference needs H2D + D2H + sync,
+ *            nvector_cuda.cu:2277-2411) and no atomics on doubles
+ *            (sundials_cuda_kernels.cuh:417-424 is order-nondeterministic).
+ *
+ * Exact-order path: for n <= exact_threshold (default 1024) one CTA stages the
+ * per-element terms in shared memory and thread 0 adds them strictly
+ * left-to-right -- bit-identical to nvector_serial.c's loops, which is what
+ * keeps integrator step/iteration counts identical to the CPU reference on the
+ * small regression problems (cvDiurnal_kry N=200, ark_heat2D N=1024).
+ *
+ * Arithmetic per term follows serial exactly (e.g. prodi = x*w; sum += prodi*prodi,
+ * serial:664-665 -- NOT x*w*x*w as VectorKernels.cuh:167 computes).
+ * HBM bytes per element: dot/wsqrsum 16, masked 24, maxnorm/min/l1 8,
+ * invtest/minquotient 16, constrmask 24, multi-dot 8(nv+1).
+ */
+#include "b200vec_device.cuh"
+
+namespace b200 {
+
+/* --------------------------------------------------------------- policies
+ * term(x0,x1,x2, outv, store) -> contribution; outv/store only if HAS_OUT  */
+struct RDot
+{
+  using Comb = CombSum;
+  static constexpr int NIN = 2;
+  static constexpr bool HAS_OUT = false;
+  __device__ double term(double x, double y, double, double&, bool&) const { return x * y; }
+};
+struct RMaxNorm
+{
+  using Comb = CombMax;
+  static constexpr int NIN = 1;
+  static constexpr bool HAS_OUT = false;
+  __device__ double term(double x, double, double, double&, bool&) const { return fabs(x); }
+};
+struct RMin
+{
+  using Comb = CombMin;
+  static constexpr int NIN = 1;
+  static constexpr bool HAS_OUT = false;
+  __device__ double term(double x, double, double, double&, bool&) const { return x; }
+};
+struct RL1
+{
+  using Comb = CombSum;
+  static constexpr int NIN = 1;
+  static constexpr bool HAS_OUT = false;
+  __device__ double term(double x, double, double, double&, bool&) const { return fabs(x); }
+};
+struct RWSqr
+{
+  using Comb = CombSum;
+  static constexpr int NIN = 2;
+  static constexpr bool HAS_OUT = false;
+  __device__ double term(double x, double w, double, double&, bool&) const
+  {
+    const double p = x * w;
+    return p * p;
+  }
+};
+struct RWSqrMask
+{
+  using Comb = CombSum;
+  static constexpr int NIN = 3;
+  static constexpr bool HAS_OUT = false;
+  __device__ double term(double x, double w, double id, double&, bool&) const
+  {
+    const double p = x * w;
+    return (id > 0.0) ? p * p : 0.0; /* adding +0.0 to a non-negative sum is exact */
+  }
+};
+/* flag reductions: value 1.0 = "ok", combined with min */
+struct RInvTest
+{
+  using Comb = CombMin;
+  static constexpr int NIN = 1;
+  static constexpr bool HAS_OUT = true;
+  __device__ double term(double x, double, double, double& outv, bool& store) const
+  {
+    store = (x != 0.0);
+    outv  = 1.0 / x;
+    return store ? 1.0 : 0.0;
+  }
+};
+struct RConstrMask
+{
+  using Comb = CombMin;
+  static constexpr int NIN = 2;
+  static constexpr bool HAS_OUT = true;
+  __device__ double term(double c, double x, double, double& outv, bool& store) const
+  {
+    store          = true;
+    const double s = x * c;
+    const double ac = fabs(c);
+    const bool viol = (c != 0.0) && ((ac > 1.5 && s <= 0.0) || (ac > 0.5 && s < 0.0));
+    outv            = viol ? 1.0 : 0.0;
+    return viol ? 0.0 : 1.0;
+  }
+};
+struct RMinQuot
+{
+  using Comb = CombMin;
+  static constexpr int NIN = 2;
+  static constexpr bool HAS_OUT = false;
+  __device__ double term(double num, double den, double, double&, bool&) const
+  {
+    return (den == 0.0) ? DBL_MAX : num / den;
+  }
+};
+
+struct RedPtrs
+{
+  const double* p0;
+  const double* p1;
+  const double* p2;
+  double* out;
+};
+
+/* stage 2: executed by every CTA after it has its value in thread 0 */
+template <class C>
+__device__ __forceinline__ void finish_block(double v, double* partials, unsigned int* counter, double* d_res,
+                                             double* h_res, double* smem)
+{
+  __shared__ bool s_last;
+  if (gridDim.x == 1)
+  {
+    if (threadIdx.x == 0)
+    {
+      *d_res = v;
+      *h_res = v;
+    }
+    return;
+  }
+  if (threadIdx.x == 0)
+  {
+    partials[blockIdx.x] = v;
+    __threadfence();
+    const unsigned int ticket = atomicAdd(counter, 1u);
+    s_last                    = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double a = C::identity();
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) a = C::apply(a, __ldcg(partials + i));
+  a = block_combine<C>(a, smem);
+  if (threadIdx.x == 0)
+  {
+    *d_res   = a;
+    *h_res   = a;
+    *counter = 0u; /* self-resetting for the next launch on this stream */
+  }
+}
+
+template <int W, int U, class R>
+__global__ void __launch_bounds__(kBlock)
+  k_reduce(R r, RedPtrs p, int64_t n, double* partials, unsigned int* counter, double* d_res, double* h_res)
+{
+  using C = typename R::Comb;
+  __shared__ double smem[kBlock / 32];
+  constexpr int64_t TILE = (int64_t)kBlock * W * U;
+  constexpr int64_t STEP = (int64_t)kBlock * W;
+  const int64_t nfull    = n / TILE;
+
+  double acc[W];
+#pragma unroll
+  for (int w = 0; w < W; w++) acc[w] = C::identity();
+
+  for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
+  {
+    const int64_t base = t * TILE + (int64_t)threadIdx.x * W;
+    double a[U][W], b[U][W], c[U][W];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+    {
+      ldg<W>(p.p0 + base + u * STEP, a[u]);
+      if (R::NIN >= 2) ldg<W>(p.p1 + base + u * STEP, b[u]);
+      if (R::NIN >= 3) ldg<W>(p.p2 + base + u * STEP, c[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+    {
+      double o[W];
+      bool st[W];
+      bool all = true;
+#pragma unroll
+      for (int w = 0; w < W; w++)
+      {
+        st[w]          = false;
+        const double v = r.term(a[u][w], R::NIN >= 2 ? b[u][w] : 0.0, R::NIN >= 3 ? c[u][w] : 0.0, o[w], st[w]);
+        acc[w]         = C::apply(acc[w], v);
+        all            = all && st[w];
+      }
+      if (R::HAS_OUT)
+      {
+        double* q = p.out + base + u * STEP;
+        if (all) stg<W>(q, o);
+        else
+        {
+#pragma unroll
+          for (int w = 0; w < W; w++)
+            if (st[w]) q[w] = o[w];
+        }
+      }
+    }
+  }
+
+  const int64_t tail0 = nfull * TILE;
+  if (tail0 < n && blockIdx.x == (unsigned)(nfull % gridDim.x))
+  {
+    for (int64_t i = tail0 + threadIdx.x; i < n; i += kBlock)
+    {
+      double o;
+      bool st        = false;
+      const double v = r.term(p.p0[i], R::NIN >= 2 ? p.p1[i] : 0.0, R::NIN >= 3 ? p.p2[i] : 0.0, o, st);
+      acc[0]         = C::apply(acc[0], v);
+      if (R::HAS_OUT && st) p.out[i] = o;
+    }
+  }
+
+  double v = acc[0];
+#pragma unroll
+  for (int w = 1; w < W; w++) v = C::apply(v, acc[w]);
+  v = block_combine<C>(v, smem);
+  finish_block<C>(v, partials, counter, d_res, h_res, smem);
+}
+
+/* exact-order path: one CTA, terms staged in shared memory, thread 0 folds
+   them left-to-right exactly as the serial loop does */
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, double* d_res, double* h_res)
+{
+  using C = typename R::Comb;
+  __shared__ double buf[kExactMaxElems];
+  for (int i = threadIdx.x; i < n; i += kBlock)
+  {
+    double o;
+    bool st = false;
+    buf[i]  = r.term(p.p0[i], R::NIN >= 2 ? p.p1[i] : 0.0, R::NIN >= 3 ? p.p2[i] : 0.0, o, st);
+    if (R::HAS_OUT && st) p.out[i] = o;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    double a = C::identity();
+#pragma unroll 8
+    for (int i = 0; i < n; i++) a = C::apply(a, buf[i]);
+    *d_res = a;
+    *h_res = a;
+  }
+}
+
+/* finish a reduction call: optional sync + copy of `count` pinned slots */
+int finish_reduction(b200vec_ctx ctx, int count, double* result_host)
+{
+  if (!result_host) return B200VEC_OK;
+  int rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(reduction)");
+  if (rc) return rc;
+  for (int i = 0; i < count; i++) result_host[i] = ctx->h_result[i];
+  return B200VEC_OK;
+}
+
+template <class R>
+static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int64_t n, double empty_value,
+                         double* result_host)
+{
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = ctx->stream;
+  if (n == 0)
+  {
+    /* nothing to read: publish the identity (N_VMin on an empty vector is
+       undefined in the reference, serial:715; we return DBL_MAX) */
+    ctx->h_result[0] = empty_value;
+    int rc = check_cuda(cudaMemcpyAsync(ctx->d_result, ctx->h_result, sizeof(double), cudaMemcpyHostToDevice, s),
+                        "cudaMemcpyAsync(empty reduction)");
+    if (rc) return rc;
+    rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    if (rc) return rc;
+    if (result_host) *result_host = empty_value;
+    return B200VEC_OK;
+  }
+  if (n <= ctx->tune.exact_threshold)
+  {
+    k_reduce_exact<R><<<1, kBlock, 0, s>>>(r, p, (int)n, ctx->d_result, ctx->h_result_dev);
+  }
+  else
+  {
+    int wmax = align_width(p.p0);
+    wmax     = min(wmax, align_width(p.p1));
+    wmax     = min(wmax, align_width(p.p2));
+    wmax     = min(wmax, align_width(p.out));
+    const MapCfg c = pick_map_cfg(ctx, n, wmax);
+#define B200_RED_CASE(WW, UU)                                                                          \
+  if (c.W == WW && c.U == UU)                                                                          \
+  k_reduce<WW, UU, R><<<c.grid, kBlock, 0, s>>>(r, p, n, ctx->d_partials, ctx->d_count, ctx->d_result, \
+                                                ctx->h_result_dev)
+    B200_RED_CASE(4, 4);
+    else B200_RED_CASE(4, 2);
+    else B200_RED_CASE(4, 1);
+    else B200_RED_CASE(2, 4);
+    else B200_RED_CASE(2, 2);
+    else B200_RED_CASE(2, 1);
+    else B200_RED_CASE(1, 4);
+    else B200_RED_CASE(1, 2);
+    else B200_RED_CASE(1, 1);
+#undef B200_RED_CASE
+  }
+  int rc = check_launch(ctx, name);
+  if (rc) return rc;
+  return finish_reduction(ctx, 1, result_host);
+}
+
+/* ------------------------------------------------------ multi-output family
+ * MODE 0: d_j = sum x * A_j            (DotProdMulti; shared = x)
+ * MODE 1: d_j = sum (A_j * B_j)^2      (WrmsNormVectorArray)
+ * MODE 2: same, masked by shared > 0   (WrmsNormMaskVectorArray; shared = id)
+ * Up to kMaxOut outputs per launch; the shared operand is read once per
+ * element and every A_j/B_j exactly once. */
+struct MultiArgs
+{
+  const double* shared;
+  const double* A[kMaxOut];
+  const double* B[kMaxOut];
+  int nout;
+};
+
+template <int MODE>
+__device__ __forceinline__ double multi_term(double sh, double a, double b)
+{
+  if (MODE == 0) return sh * a;
+  const double p = a * b;
+  if (MODE == 1) return p * p;
+  return (sh > 0.0) ? p * p : 0.0;
+}
+
+template <int W, int MODE>
+__global__ void __launch_bounds__(kBlock)
+  k_reduce_multi(const __grid_constant__ MultiArgs m, int64_t n, double* partials, unsigned int* counter,
+                 double* d_res, double* h_res)
+{
+  __shared__ double smem[kBlock / 32];
+  __shared__ bool s_last;
+  constexpr int64_t TILE = (int64_t)kBlock * W;
+  const int64_t nfull    = n / TILE;
+  const int nout         = m.nout;
+
+  double acc[kMaxOut];
+#pragma unroll
+  for (int j = 0; j < kMaxOut; j++) acc[j] = 0.0;
+
+  for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
+  {
+    const int64_t base = t * TILE + (int64_t)threadIdx.x * W;
+    double sh[W], a[kMaxOut][W], b[kMaxOut][W];
+    if (MODE != 1) ldg<W>(m.shared + base, sh);
+#pragma unroll
+    for (int j = 0; j < kMaxOut; j++)
+      if (j < nout)
+      {
+        ldg<W>(m.A[j] + base, a[j]);
+        if (MODE != 0) ldg<W>(m.B[j] + base, b[j]);
+      }
+#pragma unroll
+    for (int j = 0; j < kMaxOut; j++)
+      if (j < nout)
+      {
+#pragma unroll
+        for (int w = 0; w < W; w++)
+          acc[j] += multi_term<MODE>(MODE != 1 ? sh[w] : 0.0, a[j][w], MODE != 0 ? b[j][w] : 0.0);
+      }
+  }
+
+  const int64_t tail0 = nfull * TILE;
+  if (tail0 < n && blockIdx.x == (unsigned)(nfull % gridDim.x))
+  {
+    for (int64_t i = tail0 + threadIdx.x; i < n; i += kBlock)
+    {
+      const double sh = (MODE != 1) ? m.shared[i] : 0.0;
+#pragma unroll
+      for (int j = 0; j < kMaxOut; j++)
+        if (j < nout) acc[j] += multi_term<MODE>(sh, m.A[j][i], MODE != 0 ? m.B[j][i] : 0.0);
+    }
+  }
+
+  /* CTA value of every output -> partials[j][block] (thread 0) */
+#pragma unroll
+  for (int j = 0; j < kMaxOut; j++)
+    if (j < nout)
+    {
+      const double v = block_combine<CombSum>(acc[j], smem);
+      if (threadIdx.x == 0)
+      {
+        if (gridDim.x == 1)
+        {
+          d_res[j] = v;
+          h_res[j] = v;
+        }
+        else partials[(size_t)j * kMaxPartialBlocks + blockIdx.x] = v;
+      }
+    }
+  if (gridDim.x == 1) return;
+
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    const unsigned int ticket = atomicAdd(counter, 1u);
+    s_last                    = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int j = 0; j < nout; j++)
+  {
+    const double* row = partials + (size_t)j * kMaxPartialBlocks;
+    double a          = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) a += __ldcg(row + i);
+    a = block_combine<CombSum>(a, smem);
+    if (threadIdx.x == 0)
+    {
+      d_res[j] = a;
+      h_res[j] = a;
+    }
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+/* exact-order multi: n * nout <= kExactMaxElems; thread j folds column j */
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+  k_reduce_multi_exact(const __grid_constant__ MultiArgs m, int n, double* d_res, double* h_res)
+{
+  __shared__ double buf[kExactMaxElems];
+  const int nout = m.nout;
+  for (int i = threadIdx.x; i < n; i += kBlock)
+  {
+    const double sh = (MODE != 1) ? m.shared[i] : 0.0;
+    for (int j = 0; j < nout; j++) buf[j * n + i] = multi_term<MODE>(sh, m.A[j][i], MODE != 0 ? m.B[j][i] : 0.0);
+  }
+  __syncthreads();
+  if (threadIdx.x < nout)
+  {
+    const double* col = buf + threadIdx.x * n;
+    double a          = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < n; i++) a += col[i];
+    d_res[threadIdx.x] = a;
+    h_res[threadIdx.x] = a;
+  }
+}
+
+template <int MODE>
+static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs& m, int64_t n, int slot0)
+{
+  cudaStream_t s = ctx->stream;
+  double* d_res  = ctx->d_result + slot0;
+  double* h_res  = ctx->h_result_dev + slot0;
+  if (n <= ctx->tune.exact_threshold && n * m.nout <= kExactMaxElems)
+  {
+    k_reduce_multi_exact<MODE><<<1, kBlock, 0, s>>>(m, (int)n, d_res, h_res);
+    return check_launch(ctx, name);
+  }
+  int wmax = align_width(m.shared);
+  for (int j = 0; j < m.nout; j++)
+  {
+    wmax = min(wmax, align_width(m.A[j]));
+    wmax = min(wmax, align_width(m.B[j]));
+  }
+  int W = wmax;
+  if (ctx->tune.vec_width > 0 && ctx->tune.vec_width < W) W = (int)ctx->tune.vec_width;
+  int64_t tiles = n / ((int64_t)kBlock * W);
+  if (tiles < 1) tiles = 1;
+  const int grid = (int)((tiles < ctx->tune.max_blocks) ? tiles : ctx->tune.max_blocks);
+  if (W == 4) k_reduce_multi<4, MODE><<<grid, kBlock, 0, s>>>(m, n, ctx->d_partials, ctx->d_count, d_res, h_res);
+  else if (W == 2) k_reduce_multi<2, MODE><<<grid, kBlock, 0, s>>>(m, n, ctx->d_partials, ctx->d_count, d_res, h_res);
+  else k_reduce_multi<1, MODE><<<grid, kBlock, 0, s>>>(m, n, ctx->d_partials, ctx->d_count, d_res, h_res);
+  return check_launch(ctx, name);
+}
+
+/* nout outputs in groups of <= kMaxOut (<= fewer on the exact path so the
+   staged terms fit shared memory); results land in slots [0, nout) */
+template <int MODE>
+static int launch_multi(b200vec_ctx ctx, const char* name, int nout, const double* shared, const double* const* A,
+                        const double* const* B, int64_t n, double* result_host)
+{
+  if (nout > kMaxRows) return set_error(B200VEC_ERR_ARG, "%s: at most %d outputs per call", name, kMaxRows);
+  DeviceGuard g(ctx->device);
+  if (n == 0)
+  {
+    for (int j = 0; j < nout; j++) ctx->h_result[j] = 0.0;
+    int rc = check_cuda(cudaMemcpyAsync(ctx->d_result, ctx->h_result, sizeof(double) * nout, cudaMemcpyHostToDevice,
+                                        ctx->stream),
+                        "cudaMemcpyAsync(empty reduction)");
+    if (!rc) rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    if (!rc && result_host)
+      for (int j = 0; j < nout; j++) result_host[j] = 0.0;
+    return rc;
+  }
+  int group = kMaxOut;
+  if (n <= ctx->tune.exact_threshold)
+  {
+    int fit = (int)(kExactMaxElems / n);
+    if (fit < 1) fit = 1;
+    if (fit < group) group = fit;
+  }
+  for (int j0 = 0; j0 < nout; j0 += group)
+  {
+    MultiArgs m;
+    m.shared = shared;
+    m.nout   = (nout - j0 < group) ? nout - j0 : group;
+    for (int j = 0; j < kMaxOut; j++)
+    {
+      m.A[j] = (j < m.nout) ? A[j0 + j] : nullptr;
+      m.B[j] = (j < m.nout && B) ? B[j0 + j] : nullptr;
+    }
+    int rc = launch_multi_group<MODE>(ctx, name, m, n, j0);
+    if (rc) return rc;
+  }
+  return finish_reduction(ctx, nout, result_host);
+}
+
+} // namespace b200
+
+using namespace b200;
+
+#define B200_RARGS(cond)                                                               \
+  B200_CHECK_CTX(ctx);                                                                 \
+  if (n < 0 || (n > 0 && !(cond))) return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__)
+
+extern "C" {
+
+int b200vec_dot_prod(b200vec_ctx ctx, const double* x, const double* y, int64_t n, double* result_host)
+{
+  B200_RARGS(x && y);
+  return launch_reduce(ctx, "dot_prod", RDot{}, RedPtrs{x, y, nullptr, nullptr}, n, 0.0, result_host);
+}
+
+int b200vec_max_norm(b200vec_ctx ctx, const double* x, int64_t n, double* result_host)
+{
+  B200_RARGS(x);
+  return launch_reduce(ctx, "max_norm", RMaxNorm{}, RedPtrs{x, nullptr, nullptr, nullptr}, n, 0.0, result_host);
+}
+
+int b200vec_min(b200vec_ctx ctx, const double* x, int64_t n, double* result_host)
+{
+  B200_RARGS(x);
+  return launch_reduce(ctx, "min", RMin{}, RedPtrs{x, nullptr, nullptr, nullptr}, n, DBL_MAX, result_host);
+}
+
+int b200vec_l1_norm(b200vec_ctx ctx, const double* x, int64_t n, double* result_host)
+{
+  B200_RARGS(x);
+  return launch_reduce(ctx, "l1_norm", RL1{}, RedPtrs{x, nullptr, nullptr, nullptr}, n, 0.0, result_host);
+}
+
+int b200vec_wsqr_sum(b200vec_ctx ctx, const double* x, const double* w, int64_t n, double* result_host)
+{
+  B200_RARGS(x && w);
+  return launch_reduce(ctx, "wsqr_sum", RWSqr{}, RedPtrs{x, w, nullptr, nullptr}, n, 0.0, result_host);
+}
+
+int b200vec_wsqr_sum_mask(b200vec_ctx ctx, const double* x, const double* w, const double* id, int64_t n,
+                          double* result_host)
+{
+  B200_RARGS(x && w && id);
+  return launch_reduce(ctx, "wsqr_sum_mask", RWSqrMask{}, RedPtrs{x, w, id, nullptr}, n, 0.0, result_host);
+}
+
+int b200vec_inv_test(b200vec_ctx ctx, const double* x, double* z, int64_t n, double* result_host)
+{
+  B200_RARGS(x && z);
+  return launch_reduce(ctx, "inv_test", RInvTest{}, RedPtrs{x, nullptr, nullptr, z}, n, 1.0, result_host);
+}
+
+int b200vec_constr_mask(b200vec_ctx ctx, const double* c, const double* x, double* m, int64_t n, double* result_host)
+{
+  B200_RARGS(c && x && m);
+  return launch_reduce(ctx, "constr_mask", RConstrMask{}, RedPtrs{c, x, nullptr, m}, n, 1.0, result_host);
+}
+
+int b200vec_min_quotient(b200vec_ctx ctx, const double* num, const double* denom, int64_t n, double* result_host)
+{
+  B200_RARGS(num && denom);
+  return launch_reduce(ctx, "min_quotient", RMinQuot{}, RedPtrs{num, denom, nullptr, nullptr}, n, DBL_MAX,
+                       result_host);
+}
+
+int b200vec_dot_prod_multi(b200vec_ctx ctx, int nvec, const double* x, const double* const* Y, int64_t n,
+                           double* result_host)
+{
+  B200_CHECK_CTX(ctx);
+  if (nvec < 1 || n < 0 || !Y || (n > 0 && !x)) return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__);
+  /* nvec == 1 is N_VDotProd in the reference (serial:1007-1012): same kernel family */
+  if (nvec == 1) return b200vec_dot_prod(ctx, x, Y[0], n, result_host);
+  return launch_multi<0>(ctx, "dot_prod_multi", nvec, x, Y, nullptr, n, result_host);
+}
+
+int b200vec_wsqr_sum_vector_array(b200vec_ctx ctx, int nvec, const double* const* X, const double* const* W,
+                                  const double* id, int64_t n, double* result_host)
+{
+  B200_CHECK_CTX(ctx);
+  if (nvec < 1 || n < 0 || !X || !W) return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__);
+  if (nvec == 1)
+    return id ? b200vec_wsqr_sum_mask(ctx, X[0], W[0], id, n, result_host)
+              : b200vec_wsqr_sum(ctx, X[0], W[0], n, result_host);
+  if (id) return launch_multi<2>(ctx, "wsqr_sum_mask_vector_array", nvec, id, X, W, n, result_host);
+  return launch_multi<1>(ctx, "wsqr_sum_vector_array", nvec, nullptr, X, W, n, result_host);
+}
+
+} /* extern "C" */

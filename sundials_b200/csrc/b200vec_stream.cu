@@ -1,0 +1,236 @@
+/* b200vec_stream.cu -- streaming (elementwise) N_Vector kernels for sm_100a.
+ *
+ * One kernel template, k_map<W,U,NIN,F>: every CTA walks tiles of
+ * 256 threads x U loads x W doubles grid-stride; per tile a thread first issues
+ * all its U (x NIN operands) wide loads (256-bit LDG when the operands are
+ * 32-byte aligned), then applies the functor, then issues the U wide stores.
+ * Operands may alias the output (in-place forms of the reference): a thread
+ * only ever writes indices it has already read, so no __restrict__ anywhere.
+ *
+ * Arithmetic: compiled with -fmad=false and written in the exact operation
+ * order of nvector_serial.c, so results are bit-identical to the reference CPU
+ * vector.  The host launchers reproduce the reference's scalar/aliasing case
+ * analysis (serial:387-480, 531-555) to pick the same algebraic form.
+ *
+ * HBM roofline per element (fp64): LinearSum/Prod/Div 24 B, Scale/Abs/Inv/
+ * AddConst/Compare 16 B, Const 8 B.
+ */
+#include "b200vec_device.cuh"
+
+namespace b200 {
+
+/* ------------------------------------------------------------- functors */
+struct FSum      { __device__ double operator()(double x, double y) const { return x + y; } };
+struct FDiff     { __device__ double operator()(double x, double y) const { return x - y; } };
+struct FLin1     { double a; __device__ double operator()(double x, double y) const { return (a * x) + y; } };
+struct FLin2     { double a; __device__ double operator()(double x, double y) const { return (a * x) - y; } };
+struct FScaleSum { double c; __device__ double operator()(double x, double y) const { return c * (x + y); } };
+struct FScaleDiff{ double c; __device__ double operator()(double x, double y) const { return c * (x - y); } };
+struct FGeneral  { double a, b; __device__ double operator()(double x, double y) const { return (a * x) + (b * y); } };
+struct FProd     { __device__ double operator()(double x, double y) const { return x * y; } };
+struct FDiv      { __device__ double operator()(double x, double y) const { return x / y; } };
+struct FConst    { double c; __device__ double operator()(double, double) const { return c; } };
+struct FCopy     { __device__ double operator()(double x, double) const { return x; } };
+struct FNeg      { __device__ double operator()(double x, double) const { return -x; } };
+struct FScale    { double c; __device__ double operator()(double x, double) const { return c * x; } };
+struct FAbs      { __device__ double operator()(double x, double) const { return fabs(x); } };
+struct FInv      { __device__ double operator()(double x, double) const { return 1.0 / x; } };
+struct FAddConst { double b; __device__ double operator()(double x, double) const { return x + b; } };
+struct FCompare  { double c; __device__ double operator()(double x, double) const { return (fabs(x) >= c) ? 1.0 : 0.0; } };
+
+/* --------------------------------------------------------------- kernel */
+template <int W, int U, int NIN, class F>
+__global__ void __launch_bounds__(kBlock) k_map(F f, const double* p0, const double* p1, double* out, int64_t n)
+{
+  constexpr int64_t TILE = (int64_t)kBlock * W * U;
+  constexpr int64_t STEP = (int64_t)kBlock * W;
+  const int64_t nfull    = n / TILE;
+
+  for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
+  {
+    const int64_t base = t * TILE + (int64_t)threadIdx.x * W;
+    double a[U][W], b[U][W];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+    {
+      if (NIN >= 1) ldg<W>(p0 + base + u * STEP, a[u]);
+      if (NIN >= 2) ldg<W>(p1 + base + u * STEP, b[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+    {
+      double r[W];
+#pragma unroll
+      for (int w = 0; w < W; w++) r[w] = f(NIN >= 1 ? a[u][w] : 0.0, NIN >= 2 ? b[u][w] : 0.0);
+      stg<W>(out + base + u * STEP, r);
+    }
+  }
+
+  /* ragged tail (< TILE elements): scalar, by the least-loaded CTA */
+  const int64_t tail0 = nfull * TILE;
+  if (tail0 < n && blockIdx.x == (unsigned)(nfull % gridDim.x))
+  {
+    for (int64_t i = tail0 + threadIdx.x; i < n; i += kBlock)
+    {
+      double x = 0.0, y = 0.0;
+      if (NIN >= 1) x = p0[i];
+      if (NIN >= 2) y = p1[i];
+      out[i] = f(x, y);
+    }
+  }
+}
+
+/* ------------------------------------------------------------ launchers */
+/* widest load the alignment allows (capped by tuning), deepest unroll that
+   still leaves >= 4 tiles per SM, grid = min(tiles, max_blocks) */
+MapCfg pick_map_cfg(b200vec_ctx ctx, int64_t n, int wmax)
+{
+  MapCfg c;
+  c.W = wmax;
+  if (ctx->tune.vec_width > 0 && ctx->tune.vec_width < c.W) c.W = (int)ctx->tune.vec_width;
+  if (ctx->tune.unroll > 0) c.U = (int)ctx->tune.unroll;
+  else
+  {
+    c.U = 4;
+    while (c.U > 1 && n / ((int64_t)kBlock * c.W * c.U) < 4 * kSMs) c.U >>= 1;
+  }
+  int64_t tiles = n / ((int64_t)kBlock * c.W * c.U);
+  if (tiles < 1) tiles = 1;
+  c.grid = (int)((tiles < ctx->tune.max_blocks) ? tiles : ctx->tune.max_blocks);
+  return c;
+}
+
+template <int NIN, class F>
+static int launch_map(b200vec_ctx ctx, const char* name, F f, const double* p0, const double* p1, double* out,
+                      int64_t n)
+{
+  if (n == 0) return B200VEC_OK;
+  int wmax = align_width(out);
+  if (NIN >= 1) wmax = min(wmax, align_width(p0));
+  if (NIN >= 2) wmax = min(wmax, align_width(p1));
+  const MapCfg c = pick_map_cfg(ctx, n, wmax);
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = ctx->stream;
+#define B200_MAP_CASE(WW, UU)                                                          \
+  if (c.W == WW && c.U == UU) k_map<WW, UU, NIN, F><<<c.grid, kBlock, 0, s>>>(f, p0, p1, out, n)
+  B200_MAP_CASE(4, 4);
+  else B200_MAP_CASE(4, 2);
+  else B200_MAP_CASE(4, 1);
+  else B200_MAP_CASE(2, 4);
+  else B200_MAP_CASE(2, 2);
+  else B200_MAP_CASE(2, 1);
+  else B200_MAP_CASE(1, 4);
+  else B200_MAP_CASE(1, 2);
+  else B200_MAP_CASE(1, 1);
+#undef B200_MAP_CASE
+  return check_launch(ctx, name);
+}
+
+/* y <- s*src + y with the three sub-forms of Vaxpy (serial:1734-1760) */
+static int launch_axpy(b200vec_ctx ctx, double s, const double* src, double* acc, int64_t n)
+{
+  if (s == 1.0) return launch_map<2>(ctx, "axpy(+1)", FSum{}, acc, src, acc, n);    /* acc + src   */
+  if (s == -1.0) return launch_map<2>(ctx, "axpy(-1)", FDiff{}, acc, src, acc, n);  /* acc - src   */
+  return launch_map<2>(ctx, "axpy", FLin1{s}, src, acc, acc, n);                    /* (s*src)+acc */
+}
+
+/* the reference's case analysis, serial:397-477; z_is_x / z_is_y are HANDLE (or
+   array) identities supplied by the caller.  Shared with the vector-array op. */
+int linear_sum_dispatch(b200vec_ctx ctx, double a, const double* x, double b, const double* y, double* z,
+                        bool z_is_x, bool z_is_y, int64_t n)
+{
+  if (b == 1.0 && z_is_y) return launch_axpy(ctx, a, x, z, n);
+  if (a == 1.0 && z_is_x) return launch_axpy(ctx, b, y, z, n);
+  if (a == 1.0 && b == 1.0) return launch_map<2>(ctx, "linear_sum(sum)", FSum{}, x, y, z, n);
+  if (a == 1.0 && b == -1.0) return launch_map<2>(ctx, "linear_sum(diff)", FDiff{}, x, y, z, n);
+  if (a == -1.0 && b == 1.0) return launch_map<2>(ctx, "linear_sum(diff)", FDiff{}, y, x, z, n);
+  if (a == 1.0) return launch_map<2>(ctx, "linear_sum(lin1)", FLin1{b}, y, x, z, n);
+  if (b == 1.0) return launch_map<2>(ctx, "linear_sum(lin1)", FLin1{a}, x, y, z, n);
+  if (a == -1.0) return launch_map<2>(ctx, "linear_sum(lin2)", FLin2{b}, y, x, z, n);
+  if (b == -1.0) return launch_map<2>(ctx, "linear_sum(lin2)", FLin2{a}, x, y, z, n);
+  if (a == b) return launch_map<2>(ctx, "linear_sum(scalesum)", FScaleSum{a}, x, y, z, n);
+  if (a == -b) return launch_map<2>(ctx, "linear_sum(scalediff)", FScaleDiff{a}, x, y, z, n);
+  return launch_map<2>(ctx, "linear_sum(general)", FGeneral{a, b}, x, y, z, n);
+}
+
+/* serial:531-555 */
+int scale_dispatch(b200vec_ctx ctx, double c, const double* x, double* z, int64_t n)
+{
+  if (z == x) return launch_map<1>(ctx, "scale(inplace)", FScale{c}, x, nullptr, z, n);
+  if (c == 1.0) return launch_map<1>(ctx, "scale(copy)", FCopy{}, x, nullptr, z, n);
+  if (c == -1.0) return launch_map<1>(ctx, "scale(neg)", FNeg{}, x, nullptr, z, n);
+  return launch_map<1>(ctx, "scale", FScale{c}, x, nullptr, z, n);
+}
+
+} // namespace b200
+
+using namespace b200;
+
+#define B200_ARGS1(z)                                                                    \
+  B200_CHECK_CTX(ctx);                                                                   \
+  if (n < 0 || (n > 0 && !(z))) return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__)
+#define B200_ARGS2(x, z)                                                                 \
+  B200_CHECK_CTX(ctx);                                                                   \
+  if (n < 0 || (n > 0 && (!(x) || !(z)))) return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__)
+#define B200_ARGS3(x, y, z)                                                              \
+  B200_CHECK_CTX(ctx);                                                                   \
+  if (n < 0 || (n > 0 && (!(x) || !(y) || !(z))))                                        \
+  return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__)
+
+extern "C" {
+
+int b200vec_linear_sum(b200vec_ctx ctx, double a, const double* x, double b, const double* y, double* z, int64_t n)
+{
+  B200_ARGS3(x, y, z);
+  return linear_sum_dispatch(ctx, a, x, b, y, z, z == x, z == y, n);
+}
+
+int b200vec_const(b200vec_ctx ctx, double c, double* z, int64_t n)
+{
+  B200_ARGS1(z);
+  return launch_map<0>(ctx, "const", FConst{c}, nullptr, nullptr, z, n);
+}
+
+int b200vec_prod(b200vec_ctx ctx, const double* x, const double* y, double* z, int64_t n)
+{
+  B200_ARGS3(x, y, z);
+  return launch_map<2>(ctx, "prod", FProd{}, x, y, z, n);
+}
+
+int b200vec_div(b200vec_ctx ctx, const double* x, const double* y, double* z, int64_t n)
+{
+  B200_ARGS3(x, y, z);
+  return launch_map<2>(ctx, "div", FDiv{}, x, y, z, n);
+}
+
+int b200vec_scale(b200vec_ctx ctx, double c, const double* x, double* z, int64_t n)
+{
+  B200_ARGS2(x, z);
+  return scale_dispatch(ctx, c, x, z, n);
+}
+
+int b200vec_abs(b200vec_ctx ctx, const double* x, double* z, int64_t n)
+{
+  B200_ARGS2(x, z);
+  return launch_map<1>(ctx, "abs", FAbs{}, x, nullptr, z, n);
+}
+
+int b200vec_inv(b200vec_ctx ctx, const double* x, double* z, int64_t n)
+{
+  B200_ARGS2(x, z);
+  return launch_map<1>(ctx, "inv", FInv{}, x, nullptr, z, n);
+}
+
+int b200vec_add_const(b200vec_ctx ctx, const double* x, double b, double* z, int64_t n)
+{
+  B200_ARGS2(x, z);
+  return launch_map<1>(ctx, "add_const", FAddConst{b}, x, nullptr, z, n);
+}
+
+int b200vec_compare(b200vec_ctx ctx, double c, const double* x, double* z, int64_t n)
+{
+  B200_ARGS2(x, z);
+  return launch_map<1>(ctx, "compare", FCompare{c}, x, nullptr, z, n);
+}
+
+} /* extern "C" */
