@@ -1,0 +1,80 @@
+"""The reference's OWN tests and examples, compiled by path and unmodified,
+running on NVECTOR_B200 through the N_Vector_Ops table (tests/c/Makefile):
+
+  * test_nvector.c  -- the reference's known-answer harness for every op,
+    all three memory kinds, fused ops disabled (generic fallback) and enabled;
+  * SUNModifiedGS / SUNClassicalGS (sundials_iterative.c) serial vs B200;
+  * SPGMR / SPFGMR / PCG unit tests (1e-13 solves, both Gram-Schmidt types);
+  * CVODE cvDiurnal_kry, ARKODE ark_heat1D + ark_heat2D, IDA idaHeat2D_kry,
+    KINSOL kinFoodWeb_kry + kinLaplace_picard_kry.
+
+The integrator programs must print output BYTE-IDENTICAL to the goldens that the
+same sources produced on the reference's nvector_serial
+(tests/golden/examples/*.out, tests/golden/make_example_golden.py): same
+solution digits, same step / iteration / failure counters.  That holds because
+streaming ops are bit-exact and, at these problem sizes (N <= 1024), reductions
+take the exact-order path.
+"""
+import json
+import subprocess
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+BIN = ROOT / "oracle" / "_ref" / "bin"
+GOLD = ROOT / "tests" / "golden" / "examples"
+MANIFEST = json.loads((GOLD / "MANIFEST.json").read_text())
+
+
+def _run(exe, *args, timeout=600):
+    p = BIN / exe
+    assert p.exists(), f"{p} missing: run `make -C tests/c` where /root/reference exists"
+    return subprocess.run([str(p), *map(str, args)], capture_output=True, text=True, timeout=timeout)
+
+
+@pytest.mark.parametrize("length", [1000, 100_000])
+def test_reference_nvector_unit_harness(length):
+    r = _run("test_nvector_b200", length, 0)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "SUCCESS: NVECTOR_B200 module passed all tests" in r.stdout
+    assert "FAILED" not in r.stdout
+    # every op of the table was exercised (3 memory kinds x PASSED lines)
+    assert r.stdout.count("PASSED test -- N_VLinearCombination Case") >= 3 * 2 * 3
+
+
+def test_reference_nvector_unit_harness_tiny_lengths():
+    # the reference CUDA driver's CTest lengths (cuda/CMakeLists.txt:24-26) start at 3
+    for length in (7, 33):
+        r = _run("test_nvector_b200", length, 0, "device")
+        assert r.returncode == 0 and "SUCCESS" in r.stdout, r.stdout[-2000:]
+
+
+def test_gram_schmidt_bit_identical_small():
+    r = _run("test_gs_b200", 1000, 10, 0)
+    assert r.returncode == 0, r.stdout
+    assert "SUCCESS" in r.stdout and "MISMATCH" not in r.stdout
+
+
+def test_gram_schmidt_tolerance_large():
+    r = _run("test_gs_b200", 300_000, 20, 1e-13)
+    assert r.returncode == 0, r.stdout
+    assert "SUCCESS" in r.stdout
+
+
+@pytest.mark.parametrize("tag", sorted(MANIFEST))
+def test_reference_program_output_identical_to_serial_golden(tag):
+    e = MANIFEST[tag]
+    r = _run(e["program"] + "_b200", *e["args"])
+    want = (GOLD / f"{tag}.out").read_text()
+    assert r.returncode == e["returncode"], r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout == want, _first_diff(r.stdout, want)
+
+
+def _first_diff(a, b):
+    for i, (x, y) in enumerate(zip(a.splitlines(), b.splitlines())):
+        if x != y:
+            return f"line {i + 1}:\n  b200  : {x}\n  serial: {y}"
+    return f"length differs: {len(a)} vs {len(b)}"
