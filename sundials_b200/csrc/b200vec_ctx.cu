@@ -174,6 +174,11 @@ int b200vec_ctx_set_tuning(b200vec_ctx ctx, const char* key, int64_t value)
       return set_error(B200VEC_ERR_ARG, "max_blocks must be in [1,%d]", kMaxPartialBlocks);
     ctx->tune.max_blocks = value;
   }
+  else if (!strcmp(key, "stream_max_blocks"))
+  {
+    if (value < 0 || value > 0x7fffffff) return set_error(B200VEC_ERR_ARG, "stream_max_blocks must be >= 0");
+    ctx->tune.stream_max_blocks = value;
+  }
   else if (!strcmp(key, "vec_width"))
   {
     if (value != 0 && value != 1 && value != 2 && value != 4)
@@ -205,6 +210,7 @@ int64_t b200vec_ctx_get_tuning(b200vec_ctx ctx, const char* key)
 {
   if (!ctx || !key) return -1;
   if (!strcmp(key, "max_blocks")) return ctx->tune.max_blocks;
+  if (!strcmp(key, "stream_max_blocks")) return ctx->tune.stream_max_blocks;
   if (!strcmp(key, "vec_width")) return ctx->tune.vec_width;
   if (!strcmp(key, "unroll")) return ctx->tune.unroll;
   if (!strcmp(key, "exact_threshold")) return ctx->tune.exact_threshold;

@@ -253,9 +253,10 @@ __global__ void __launch_bounds__(kBlock)
 /* grid.x for a row kernel: spread max_blocks CTAs over the rows */
 static int rows_grid_x(b200vec_ctx ctx, int64_t tiles, int nrows)
 {
-  int64_t per_row = ctx->tune.max_blocks / nrows;
-  if (per_row < 1) per_row = 1;
   if (tiles < 1) tiles = 1;
+  if (ctx->tune.stream_max_blocks <= 0) return (int)((tiles < 0x7fffffff) ? tiles : 0x7fffffff);
+  int64_t per_row = ctx->tune.stream_max_blocks / nrows;
+  if (per_row < 1) per_row = 1;
   return (int)((tiles < per_row) ? tiles : per_row);
 }
 
@@ -380,7 +381,7 @@ static int map_rows(b200vec_ctx ctx, const char* name, int nrows, const double* 
       m.s[r]   = s_host ? s_host[r0 + r] : 0.0;
       wmax     = min(wmax, min(align_width(m.p0[r]), min(align_width(m.p1[r]), align_width(m.out[r]))));
     }
-    MapCfg c = pick_map_cfg(ctx, n, wmax);
+    MapCfg c = pick_map_cfg(ctx, n, wmax, false);
     const int U = (c.U >= 4) ? 4 : 1;
     dim3 grid(rows_grid_x(ctx, n / ((int64_t)kBlock * c.W * U), nr), nr);
     cudaStream_t s = ctx->stream;

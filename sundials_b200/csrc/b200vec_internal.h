@@ -23,7 +23,8 @@ constexpr int kExactMaxElems = 4096; /* smem doubles available to the exact-orde
 
 struct Tuning
 {
-  int64_t max_blocks      = kMaxBlocksDef;
+  int64_t max_blocks      = kMaxBlocksDef; /* reductions (partials rows)              */
+  int64_t stream_max_blocks = 0;           /* streaming kernels; 0 = one tile per CTA  */
   int64_t vec_width       = 0; /* 0 = auto (widest the alignment allows) */
   int64_t unroll          = 0; /* 0 = auto */
   int64_t exact_threshold = 1024;
@@ -73,7 +74,7 @@ struct MapCfg
   int U;    /* independent wide loads in flight per operand and thread        */
   int grid; /* CTAs                                                           */
 };
-MapCfg pick_map_cfg(b200vec_ctx ctx, int64_t n, int wmax);
+MapCfg pick_map_cfg(b200vec_ctx ctx, int64_t n, int wmax, bool reduction);
 static inline int align_width(const void* p)
 {
   if (!p) return 4; /* absent operand does not constrain */

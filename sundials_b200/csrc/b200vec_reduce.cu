@@ -302,7 +302,7 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
     wmax     = min(wmax, align_width(p.p1));
     wmax     = min(wmax, align_width(p.p2));
     wmax     = min(wmax, align_width(p.out));
-    const MapCfg c = pick_map_cfg(ctx, n, wmax);
+    const MapCfg c = pick_map_cfg(ctx, n, wmax, true);
 #define B200_RED_CASE(WW, UU)                                                                          \
   if (c.W == WW && c.U == UU)                                                                          \
   k_reduce<WW, UU, R><<<c.grid, kBlock, 0, s>>>(r, p, n, ctx->d_partials, ctx->d_count, ctx->d_result, \

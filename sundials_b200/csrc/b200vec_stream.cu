@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kBlock) k_map(F f, const double* p0, const dou
 /* ------------------------------------------------------------ launchers */
 /* widest load the alignment allows (capped by tuning), deepest unroll that
    still leaves >= 4 tiles per SM, grid = min(tiles, max_blocks) */
-MapCfg pick_map_cfg(b200vec_ctx ctx, int64_t n, int wmax)
+MapCfg pick_map_cfg(b200vec_ctx ctx, int64_t n, int wmax, bool reduction)
 {
   MapCfg c;
   c.W = wmax;
@@ -96,7 +96,12 @@ MapCfg pick_map_cfg(b200vec_ctx ctx, int64_t n, int wmax)
   }
   int64_t tiles = n / ((int64_t)kBlock * c.W * c.U);
   if (tiles < 1) tiles = 1;
-  c.grid = (int)((tiles < ctx->tune.max_blocks) ? tiles : ctx->tune.max_blocks);
+  /* streaming: one tile per CTA unless capped (measured best on B200: the block
+     scheduler back-fills SMs as CTAs retire, no tail quantisation); reductions:
+     a fixed cap, because every CTA adds a row to the fixed-order final pass */
+  int64_t cap = reduction ? ctx->tune.max_blocks : ctx->tune.stream_max_blocks;
+  if (cap <= 0) cap = 0x7fffffff;
+  c.grid = (int)((tiles < cap) ? tiles : cap);
   return c;
 }
 
@@ -108,7 +113,7 @@ static int launch_map(b200vec_ctx ctx, const char* name, F f, const double* p0, 
   int wmax = align_width(out);
   if (NIN >= 1) wmax = min(wmax, align_width(p0));
   if (NIN >= 2) wmax = min(wmax, align_width(p1));
-  const MapCfg c = pick_map_cfg(ctx, n, wmax);
+  const MapCfg c = pick_map_cfg(ctx, n, wmax, false);
   DeviceGuard g(ctx->device);
   cudaStream_t s = ctx->stream;
 #define B200_MAP_CASE(WW, UU)                                                          \
