@@ -473,6 +473,45 @@ def b200_arm(args):
         per_op[name] = {"us": round(us, 2), "GBs": round(bpe * n / us / 1e3, 1),
                         "frac_of_peak": round(bpe * n / us / 1e3 / peak, 3)}
 
+    # reductions: the API-level time above includes the host round trip that
+    # returning a scalar requires; also time the kernels alone (C ABI, async)
+    dptr = lib.N_VGetDeviceArrayPointer_B200
+    X, Y, Z = vec["X"], vec["Y"], vec["Z"]
+    W, ID, CN = vec["W"], vec["ID"], vec["CN"]
+
+    def tab(vs):
+        return (C.c_void_p * len(vs))(*[dptr(v) for v in vs])
+
+    tX, tY = tab(X), tab(Y)
+    kernel_only = {
+        "N_VDotProd": (16, lambda: lib.b200vec_dot_prod(ctx, dptr(X[1]), dptr(Y[1]), n, None)),
+        "N_VMaxNorm": (8, lambda: lib.b200vec_max_norm(ctx, dptr(X[2]), n, None)),
+        "N_VWrmsNorm": (16, lambda: lib.b200vec_wsqr_sum(ctx, dptr(X[3]), dptr(W), n, None)),
+        "N_VWrmsNormMask": (24, lambda: lib.b200vec_wsqr_sum_mask(ctx, dptr(X[4]), dptr(W), dptr(ID), n, None)),
+        "N_VMin": (8, lambda: lib.b200vec_min(ctx, dptr(X[5]), n, None)),
+        "N_VL1Norm": (8, lambda: lib.b200vec_l1_norm(ctx, dptr(X[7]), n, None)),
+        "N_VInvTest": (16, lambda: lib.b200vec_inv_test(ctx, dptr(X[1]), dptr(Z[1]), n, None)),
+        "N_VConstrMask": (24, lambda: lib.b200vec_constr_mask(ctx, dptr(CN), dptr(X[2]), dptr(Z[2]), n, None)),
+        "N_VMinQuotient": (16, lambda: lib.b200vec_min_quotient(ctx, dptr(X[3]), dptr(Y[3]), n, None)),
+        "N_VDotProdMulti": (8 * (NVECS + 1), lambda: lib.b200vec_dot_prod_multi(ctx, NVECS, dptr(X[2]), tY, n, None)),
+        "N_VWrmsNormVectorArray": (16 * NVECS,
+                                   lambda: lib.b200vec_wsqr_sum_vector_array(ctx, NVECS, tX, tY, None, n, None)),
+        "N_VWrmsNormMaskVectorArray": (8 * (2 * NVECS + 1),
+                                       lambda: lib.b200vec_wsqr_sum_vector_array(ctx, NVECS, tX, tY, dptr(ID), n, None)),
+    }
+    for name, (bpe, fn) in kernel_only.items():
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / reps * 1e3
+        per_op[name].update({"kernel_us": round(us, 2), "kernel_GBs": round(bpe * n / us / 1e3, 1),
+                             "kernel_frac_of_peak": round(bpe * n / us / 1e3 / peak, 3)})
+
     # dominant kernel: the general N_VLinearSum form, k_map<4,4,2,FGeneral>
     dom = per_op["N_VLinearSum-9"]
     roofline = {"bound": "hbm", "kernel": "k_map<4,4,2,FGeneral> (N_VLinearSum general form)",

@@ -81,7 +81,7 @@ int b200vec_ctx_create(b200vec_ctx* out, int device, void* stream)
   if (!rc) rc = check_cuda(cudaMalloc((void**)&c->d_result, sizeof(double) * kMaxRows), "cudaMalloc(result)");
   if (!rc) rc = check_cuda(cudaMemset(c->d_result, 0, sizeof(double) * kMaxRows), "cudaMemset(result)");
   if (!rc)
-    rc = check_cuda(cudaHostAlloc((void**)&c->h_result, sizeof(double) * kMaxRows, cudaHostAllocMapped),
+    rc = check_cuda(cudaHostAlloc((void**)&c->h_result, sizeof(double) * (kMaxRows + 8), cudaHostAllocMapped),
                     "cudaHostAlloc(result)");
   if (!rc)
     rc = check_cuda(cudaHostGetDevicePointer((void**)&c->h_result_dev, c->h_result, 0),
@@ -91,7 +91,7 @@ int b200vec_ctx_create(b200vec_ctx* out, int device, void* stream)
     b200vec_ctx_release(c);
     return rc;
   }
-  memset(c->h_result, 0, sizeof(double) * kMaxRows);
+  memset(c->h_result, 0, sizeof(double) * (kMaxRows + 8));
   *out = c;
   return B200VEC_OK;
 }
@@ -197,6 +197,7 @@ int b200vec_ctx_set_tuning(b200vec_ctx ctx, const char* key, int64_t value)
       return set_error(B200VEC_ERR_ARG, "exact_threshold must be in [0,%d]", kExactMaxElems);
     ctx->tune.exact_threshold = value;
   }
+  else if (!strcmp(key, "spin_wait")) ctx->tune.spin_wait = value ? 1 : 0;
   else if (!strcmp(key, "count_launches"))
   {
     ctx->tune.count_launches = value ? 1 : 0;
@@ -215,6 +216,7 @@ int64_t b200vec_ctx_get_tuning(b200vec_ctx ctx, const char* key)
   if (!strcmp(key, "unroll")) return ctx->tune.unroll;
   if (!strcmp(key, "exact_threshold")) return ctx->tune.exact_threshold;
   if (!strcmp(key, "count_launches")) return ctx->tune.count_launches;
+  if (!strcmp(key, "spin_wait")) return ctx->tune.spin_wait;
   return -1;
 }
 

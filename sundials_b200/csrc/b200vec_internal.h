@@ -15,7 +15,7 @@ namespace b200 {
 
 constexpr int kBlock        = 256;  /* threads per CTA for every kernel               */
 constexpr int kSMs          = 148;  /* B200: 2 dies x 74 SMs                          */
-constexpr int kMaxBlocksDef = kSMs * 8; /* 8 x 256 threads = 2048 = full SM occupancy */
+constexpr int kMaxBlocksDef = kSMs * 4; /* reductions: 4 CTAs/SM measured best (sweep_reduce, profiles/) */
 constexpr int kMaxPartialBlocks = 4096; /* reduction partial rows (>= any max_blocks) */
 constexpr int kMaxOut       = 8;    /* outputs per multi-reduction launch             */
 constexpr int kMaxRows      = 64;   /* result slots per context                       */
@@ -29,6 +29,7 @@ struct Tuning
   int64_t unroll          = 0; /* 0 = auto */
   int64_t exact_threshold = 1024;
   int64_t count_launches  = 0;
+  int64_t spin_wait       = 1; /* poll the pinned sequence word instead of cudaStreamSynchronize */
 };
 
 } // namespace b200
@@ -52,6 +53,7 @@ struct b200vec_ctx_s
      stream sync and no memcpy */
   double* h_result      = nullptr; /* host address   */
   double* h_result_dev  = nullptr; /* device alias   */
+  unsigned long long seq = 0;      /* reductions launched so far; word [kMaxRows] of h_result mirrors it */
 
   /* exact-size free-list cache of device allocations (clone/destroy churn) */
   std::multimap<size_t, void*> cache;

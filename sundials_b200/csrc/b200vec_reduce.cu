@@ -129,18 +129,36 @@ struct RedPtrs
   double* out;
 };
 
+/* where a finished reduction publishes its value(s): the context's device
+   slots, their pinned host mirror, and a pinned sequence word the host can spin
+   on instead of paying a cudaStreamSynchronize round trip */
+struct ResOut
+{
+  double* d_res;
+  double* h_res;
+  volatile unsigned long long* h_flag;
+  unsigned long long seq;
+};
+
+__device__ __forceinline__ void publish_done(const ResOut& o)
+{
+  __threadfence_system(); /* results before the flag, all the way to host memory */
+  *o.h_flag = o.seq;
+}
+
 /* stage 2: executed by every CTA after it has its value in thread 0 */
 template <class C>
-__device__ __forceinline__ void finish_block(double v, double* partials, unsigned int* counter, double* d_res,
-                                             double* h_res, double* smem)
+__device__ __forceinline__ void finish_block(double v, double* partials, unsigned int* counter, const ResOut& o,
+                                             double* smem)
 {
   __shared__ bool s_last;
   if (gridDim.x == 1)
   {
     if (threadIdx.x == 0)
     {
-      *d_res = v;
-      *h_res = v;
+      *o.d_res = v;
+      *o.h_res = v;
+      publish_done(o);
     }
     return;
   }
@@ -159,15 +177,16 @@ __device__ __forceinline__ void finish_block(double v, double* partials, unsigne
   a = block_combine<C>(a, smem);
   if (threadIdx.x == 0)
   {
-    *d_res   = a;
-    *h_res   = a;
+    *o.d_res = a;
+    *o.h_res = a;
     *counter = 0u; /* self-resetting for the next launch on this stream */
+    publish_done(o);
   }
 }
 
 template <int W, int U, class R>
 __global__ void __launch_bounds__(kBlock)
-  k_reduce(R r, RedPtrs p, int64_t n, double* partials, unsigned int* counter, double* d_res, double* h_res)
+  k_reduce(R r, RedPtrs p, int64_t n, double* partials, unsigned int* counter, ResOut o)
 {
   using C = typename R::Comb;
   __shared__ double smem[kBlock / 32];
@@ -235,13 +254,13 @@ __global__ void __launch_bounds__(kBlock)
 #pragma unroll
   for (int w = 1; w < W; w++) v = C::apply(v, acc[w]);
   v = block_combine<C>(v, smem);
-  finish_block<C>(v, partials, counter, d_res, h_res, smem);
+  finish_block<C>(v, partials, counter, o, smem);
 }
 
 /* exact-order path: one CTA, terms staged in shared memory, thread 0 folds
    them left-to-right exactly as the serial loop does */
 template <class R>
-__global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, double* d_res, double* h_res)
+__global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, ResOut o)
 {
   using C = typename R::Comb;
   __shared__ double buf[kExactMaxElems];
@@ -258,16 +277,51 @@ __global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, 
     double a = C::identity();
 #pragma unroll 8
     for (int i = 0; i < n; i++) a = C::apply(a, buf[i]);
-    *d_res = a;
-    *h_res = a;
+    *o.d_res = a;
+    *o.h_res = a;
+    publish_done(o);
   }
 }
 
 /* finish a reduction call: optional sync + copy of `count` pinned slots */
+/* next sequence number + where the kernel publishes */
+static ResOut next_out(b200vec_ctx ctx, int slot0)
+{
+  ResOut o;
+  o.d_res  = ctx->d_result + slot0;
+  o.h_res  = ctx->h_result_dev + slot0;
+  o.h_flag = (volatile unsigned long long*)(ctx->h_result_dev + kMaxRows);
+  o.seq    = ++ctx->seq;
+  return o;
+}
+
 int finish_reduction(b200vec_ctx ctx, int count, double* result_host)
 {
   if (!result_host) return B200VEC_OK;
-  int rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(reduction)");
+  int rc = B200VEC_OK;
+  bool seen = false;
+  if (ctx->tune.spin_wait)
+  {
+    /* the final pass stores the scalars and then a sequence word into pinned host
+       memory: polling it costs ~1-2 us after the kernel ends, a
+       cudaStreamSynchronize round trip several times that.  Bounded spin, then
+       fall back to the sync (which also surfaces asynchronous errors). */
+    volatile unsigned long long* flag = (volatile unsigned long long*)(ctx->h_result + kMaxRows);
+    const unsigned long long want     = ctx->seq;
+    for (long spins = 0; spins < 20000000L; spins++)
+    {
+      if (*flag >= want)
+      {
+        seen = true;
+        break;
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+      if ((spins & 0xffff) == 0xffff && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) break;
+    }
+  }
+  if (!seen) rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(reduction)");
   if (rc) return rc;
   for (int i = 0; i < count; i++) result_host[i] = ctx->h_result[i];
   return B200VEC_OK;
@@ -294,7 +348,7 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
   }
   if (n <= ctx->tune.exact_threshold)
   {
-    k_reduce_exact<R><<<1, kBlock, 0, s>>>(r, p, (int)n, ctx->d_result, ctx->h_result_dev);
+    k_reduce_exact<R><<<1, kBlock, 0, s>>>(r, p, (int)n, next_out(ctx, 0));
   }
   else
   {
@@ -303,10 +357,10 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
     wmax     = min(wmax, align_width(p.p2));
     wmax     = min(wmax, align_width(p.out));
     const MapCfg c = pick_map_cfg(ctx, n, wmax, true);
+    const ResOut out = next_out(ctx, 0);
 #define B200_RED_CASE(WW, UU)                                                                          \
   if (c.W == WW && c.U == UU)                                                                          \
-  k_reduce<WW, UU, R><<<c.grid, kBlock, 0, s>>>(r, p, n, ctx->d_partials, ctx->d_count, ctx->d_result, \
-                                                ctx->h_result_dev)
+  k_reduce<WW, UU, R><<<c.grid, kBlock, 0, s>>>(r, p, n, ctx->d_partials, ctx->d_count, out)
     B200_RED_CASE(4, 4);
     else B200_RED_CASE(4, 2);
     else B200_RED_CASE(4, 1);
@@ -348,8 +402,7 @@ __device__ __forceinline__ double multi_term(double sh, double a, double b)
 
 template <int W, int MODE>
 __global__ void __launch_bounds__(kBlock)
-  k_reduce_multi(const __grid_constant__ MultiArgs m, int64_t n, double* partials, unsigned int* counter,
-                 double* d_res, double* h_res)
+  k_reduce_multi(const __grid_constant__ MultiArgs m, int64_t n, double* partials, unsigned int* counter, ResOut o)
 {
   __shared__ double smem[kBlock / 32];
   __shared__ bool s_last;
@@ -405,13 +458,17 @@ __global__ void __launch_bounds__(kBlock)
       {
         if (gridDim.x == 1)
         {
-          d_res[j] = v;
-          h_res[j] = v;
+          o.d_res[j] = v;
+          o.h_res[j] = v;
         }
         else partials[(size_t)j * kMaxPartialBlocks + blockIdx.x] = v;
       }
     }
-  if (gridDim.x == 1) return;
+  if (gridDim.x == 1)
+  {
+    if (threadIdx.x == 0) publish_done(o);
+    return;
+  }
 
   if (threadIdx.x == 0)
   {
@@ -430,17 +487,21 @@ __global__ void __launch_bounds__(kBlock)
     a = block_combine<CombSum>(a, smem);
     if (threadIdx.x == 0)
     {
-      d_res[j] = a;
-      h_res[j] = a;
+      o.d_res[j] = a;
+      o.h_res[j] = a;
     }
   }
-  if (threadIdx.x == 0) *counter = 0u;
+  if (threadIdx.x == 0)
+  {
+    *counter = 0u;
+    publish_done(o);
+  }
 }
 
 /* exact-order multi: n * nout <= kExactMaxElems; thread j folds column j */
 template <int MODE>
 __global__ void __launch_bounds__(kBlock)
-  k_reduce_multi_exact(const __grid_constant__ MultiArgs m, int n, double* d_res, double* h_res)
+  k_reduce_multi_exact(const __grid_constant__ MultiArgs m, int n, ResOut o)
 {
   __shared__ double buf[kExactMaxElems];
   const int nout = m.nout;
@@ -456,20 +517,21 @@ __global__ void __launch_bounds__(kBlock)
     double a          = 0.0;
 #pragma unroll 8
     for (int i = 0; i < n; i++) a += col[i];
-    d_res[threadIdx.x] = a;
-    h_res[threadIdx.x] = a;
+    o.d_res[threadIdx.x] = a;
+    o.h_res[threadIdx.x] = a;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) publish_done(o);
 }
 
 template <int MODE>
 static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs& m, int64_t n, int slot0)
 {
   cudaStream_t s = ctx->stream;
-  double* d_res  = ctx->d_result + slot0;
-  double* h_res  = ctx->h_result_dev + slot0;
+  const ResOut out = next_out(ctx, slot0);
   if (n <= ctx->tune.exact_threshold && n * m.nout <= kExactMaxElems)
   {
-    k_reduce_multi_exact<MODE><<<1, kBlock, 0, s>>>(m, (int)n, d_res, h_res);
+    k_reduce_multi_exact<MODE><<<1, kBlock, 0, s>>>(m, (int)n, out);
     return check_launch(ctx, name);
   }
   int wmax = align_width(m.shared);
@@ -482,10 +544,15 @@ static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs
   if (ctx->tune.vec_width > 0 && ctx->tune.vec_width < W) W = (int)ctx->tune.vec_width;
   int64_t tiles = n / ((int64_t)kBlock * W);
   if (tiles < 1) tiles = 1;
-  const int grid = (int)((tiles < ctx->tune.max_blocks) ? tiles : ctx->tune.max_blocks);
-  if (W == 4) k_reduce_multi<4, MODE><<<grid, kBlock, 0, s>>>(m, n, ctx->d_partials, ctx->d_count, d_res, h_res);
-  else if (W == 2) k_reduce_multi<2, MODE><<<grid, kBlock, 0, s>>>(m, n, ctx->d_partials, ctx->d_count, d_res, h_res);
-  else k_reduce_multi<1, MODE><<<grid, kBlock, 0, s>>>(m, n, ctx->d_partials, ctx->d_count, d_res, h_res);
+  /* register-heavy kernels (8 accumulators + 8..16 wide operands in flight): run
+     them persistent-style with exactly the resident CTA count -- 1 per SM for the
+     256-bit two-operand modes (~170 regs), 2 per SM otherwise -- measured best */
+  int64_t cap = (W == 4 && MODE != 0) ? kSMs : 2 * kSMs;
+  if (cap > ctx->tune.max_blocks) cap = ctx->tune.max_blocks;
+  const int grid = (int)((tiles < cap) ? tiles : cap);
+  if (W == 4) k_reduce_multi<4, MODE><<<grid, kBlock, 0, s>>>(m, n, ctx->d_partials, ctx->d_count, out);
+  else if (W == 2) k_reduce_multi<2, MODE><<<grid, kBlock, 0, s>>>(m, n, ctx->d_partials, ctx->d_count, out);
+  else k_reduce_multi<1, MODE><<<grid, kBlock, 0, s>>>(m, n, ctx->d_partials, ctx->d_count, out);
   return check_launch(ctx, name);
 }
 

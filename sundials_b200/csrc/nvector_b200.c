@@ -392,8 +392,8 @@ SUNErrCode N_VSetStream_B200(N_Vector v, void* stream) { return map_err(b200vec_
 
 void N_VSpace_B200(N_Vector v, sunindextype* lrw, sunindextype* liw)
 {
-  *lrw = NVC(v)->global_length;
-  *liw = 2;
+  *lrw = NVC(v)->global_length; /* serial:362-373 */
+  *liw = 1;
 }
 
 void N_VPrintFile_B200(N_Vector v, FILE* outfile)
