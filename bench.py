@@ -14,8 +14,8 @@ once, each output written once) per second, summed over the suite.
   e2e     same suite, but every step first copies the nvecs input vectors from
           pinned host memory (N_VCopyToDevice_B200) and ends with a D2H read of a
           result vector plus the reduction scalars
-  roofline  the dominant kernel (k_map<4,4,2,FGeneral>, N_VLinearSum general
-          form) timed alone with CUDA events, vs the measured HBM copy peak
+  roofline  the dominant kernel by share of the step (k_scaleadd_rows<4>) timed
+          with CUDA events, vs the measured HBM copy peak
   cpu_baseline  the reference's own nvector_openmp (all host threads) and
           nvector_serial (1 core) on a bounded sample of the same suite
   --impl reference : the reference CPU implementation alone (driver's baseline arm)
@@ -512,17 +512,29 @@ def b200_arm(args):
         per_op[name].update({"kernel_us": round(us, 2), "kernel_GBs": round(bpe * n / us / 1e3, 1),
                              "kernel_frac_of_peak": round(bpe * n / us / 1e3 / peak, 3)})
 
-    # dominant kernel: the general N_VLinearSum form, k_map<4,4,2,FGeneral>
-    dom = per_op["N_VLinearSum-9"]
-    roofline = {"bound": "hbm", "kernel": "k_map<4,4,2,FGeneral> (N_VLinearSum general form)",
-                "achieved": dom["GBs"], "peak": peak, "unit": "GB/s", "frac": round(dom["GBs"] / peak, 4),
+    # dominant kernel by share of the step (profiles/r01_launches_summary.md: 28 %):
+    # k_scaleadd_rows<4>, launched 3x per step (N_VScaleAddMulti-1/-2, 136 B/elt, and
+    # N_VScaleAddMultiVectorArray, 576 B/elt).  achieved = algorithmic bytes of
+    # those launches / their CUDA-event time, measured live above.
+    dom_ops = ["N_VScaleAddMulti-1", "N_VScaleAddMulti-2", "N_VScaleAddMultiVectorArray"]
+    dom_bytes = {name: bpe * n for name, bpe, _ in suite if name in dom_ops}
+    dom_us = sum(per_op[k]["us"] for k in dom_ops)
+    dom_gbs = sum(dom_bytes.values()) / dom_us / 1e3
+    roofline = {"bound": "hbm", "kernel": "k_scaleadd_rows<4> (N_VScaleAddMulti, N_VScaleAddMultiVectorArray)",
+                "achieved": round(dom_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(dom_gbs / peak, 4),
                 "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": 24 * n,
+                "launches_per_step": 3,
+                "algorithmic_bytes_per_launch": {k: dom_bytes[k] for k in dom_ops},
+                "avg_launch_us": round(dom_us / 3, 2),
+                "share_of_step": round(dom_us / (ms_step * 1e3), 4),
                 "suite_frac": round(value / world / peak, 4)}
-    prof = ROOT / "profiles" / "linear_sum_traffic.json"
+    prof = ROOT / "profiles" / "scaleadd_traffic.json"
     if prof.exists():
         try:
-            roofline["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+            t = json.loads(prof.read_text())
+            # ncu --set full capture of the N_VScaleAddMulti launch (nv=8, n=2^24): dram read+write per launch
+            roofline["traffic"] = t.get("dram_bytes_per_launch")
+            roofline["traffic_launch"] = t.get("kernel")
         except Exception:
             pass
 

@@ -68,7 +68,8 @@ void* b200vec_ctx_get_stream(b200vec_ctx ctx);
 int b200vec_ctx_device(b200vec_ctx ctx);
 int b200vec_ctx_sync(b200vec_ctx ctx); /* cudaStreamSynchronize on the ctx stream */
 /* tuning knobs (sweepable from the bench without recompiling):
- *  "max_blocks"      grid cap of the reduction kernels (default 148*4)
+ *  "max_blocks"      grid cap of the reduction kernels (default 148*2 CTAs of 512 threads)
+ *  "pdl"             1 (default): programmatic dependent launch on every kernel
  *  "spin_wait"       1 (default): scalar-returning ops poll a pinned sequence word
  *                    written by the kernel's final pass; 0: cudaStreamSynchronize
  *  "stream_max_blocks" grid cap of streaming/fused kernels (default 0 = one tile per CTA)

@@ -81,7 +81,7 @@ int b200vec_ctx_create(b200vec_ctx* out, int device, void* stream)
   if (!rc) rc = check_cuda(cudaMalloc((void**)&c->d_result, sizeof(double) * kMaxRows), "cudaMalloc(result)");
   if (!rc) rc = check_cuda(cudaMemset(c->d_result, 0, sizeof(double) * kMaxRows), "cudaMemset(result)");
   if (!rc)
-    rc = check_cuda(cudaHostAlloc((void**)&c->h_result, sizeof(double) * (kMaxRows + 8), cudaHostAllocMapped),
+    rc = check_cuda(cudaHostAlloc((void**)&c->h_result, sizeof(double) * kHostSlots, cudaHostAllocMapped),
                     "cudaHostAlloc(result)");
   if (!rc)
     rc = check_cuda(cudaHostGetDevicePointer((void**)&c->h_result_dev, c->h_result, 0),
@@ -91,7 +91,7 @@ int b200vec_ctx_create(b200vec_ctx* out, int device, void* stream)
     b200vec_ctx_release(c);
     return rc;
   }
-  memset(c->h_result, 0, sizeof(double) * (kMaxRows + 8));
+  memset(c->h_result, 0, sizeof(double) * kHostSlots);
   *out = c;
   return B200VEC_OK;
 }
@@ -198,6 +198,7 @@ int b200vec_ctx_set_tuning(b200vec_ctx ctx, const char* key, int64_t value)
     ctx->tune.exact_threshold = value;
   }
   else if (!strcmp(key, "spin_wait")) ctx->tune.spin_wait = value ? 1 : 0;
+  else if (!strcmp(key, "pdl")) ctx->tune.pdl = value ? 1 : 0;
   else if (!strcmp(key, "count_launches"))
   {
     ctx->tune.count_launches = value ? 1 : 0;
@@ -217,6 +218,7 @@ int64_t b200vec_ctx_get_tuning(b200vec_ctx ctx, const char* key)
   if (!strcmp(key, "exact_threshold")) return ctx->tune.exact_threshold;
   if (!strcmp(key, "count_launches")) return ctx->tune.count_launches;
   if (!strcmp(key, "spin_wait")) return ctx->tune.spin_wait;
+  if (!strcmp(key, "pdl")) return ctx->tune.pdl;
   return -1;
 }
 

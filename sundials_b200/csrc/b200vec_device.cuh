@@ -61,6 +61,15 @@ __device__ __forceinline__ void stg<4>(double* p, const double (&v)[4])
                : "memory");
 }
 
+/* ---- programmatic dependent launch: first statement(s) of every kernel.
+ * wait   = all prerequisite grids on the stream have completed and flushed;
+ * launch = the next kernel on the stream may start becoming resident. ---- */
+__device__ __forceinline__ void pdl_prologue()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 /* ---- combiners.  The predicates mirror nvector_serial.c:635,719 (strict
  * comparisons, so NaNs never win) rather than fmax/fmin. ---- */
 struct CombSum
@@ -95,9 +104,9 @@ __device__ __forceinline__ double warp_combine(double v)
 }
 
 /* block-wide combine of one value per thread; result valid in thread 0.
- * Fixed tree: lanes by shuffle, then the 8 warp leaders by shuffle in warp 0. */
-template <class C>
-__device__ __forceinline__ double block_combine(double v, double* smem /* >= kBlock/32 doubles */)
+ * Fixed tree: lanes by shuffle, then the BLOCK/32 warp leaders by shuffle in warp 0. */
+template <class C, int BLOCK = kBlock>
+__device__ __forceinline__ double block_combine(double v, double* smem /* >= BLOCK/32 doubles */)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   v = warp_combine<C>(v);
@@ -106,7 +115,7 @@ __device__ __forceinline__ double block_combine(double v, double* smem /* >= kBl
   double r = C::identity();
   if (warp == 0)
   {
-    r = (lane < kBlock / 32) ? smem[lane] : C::identity();
+    r = (lane < BLOCK / 32) ? smem[lane] : C::identity();
     r = warp_combine<C>(r);
   }
   __syncthreads();

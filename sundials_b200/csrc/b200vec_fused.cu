@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(kBlock) k_lincomb_rows(const __grid_constant__
     s_c[threadIdx.x] = a.c[threadIdx.x];
     s_x[threadIdx.x] = a.X[threadIdx.x * a.nrows + row];
   }
+  pdl_prologue(); /* parameters are staged before the wait on the previous kernel */
   __syncthreads();
   double* z = a.Z[row];
 
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(kBlock) k_scaleadd_rows(const __grid_constant_
     s_y[threadIdx.x] = a.Y[threadIdx.x * a.nrows + row];
     s_z[threadIdx.x] = a.Z[threadIdx.x * a.nrows + row];
   }
+  pdl_prologue();
   __syncthreads();
   const double* x = a.X[row];
 
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(kBlock)
   double* out            = m.out[row];
   const double s         = m.s[row];
   const int64_t nfull    = n / TILE;
+  pdl_prologue();
 
   for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
   {
@@ -306,9 +309,9 @@ static int lincomb_rows(b200vec_ctx ctx, int nterms, int nrows, const double* c,
       a.nrows  = nr;
       const int W = tuned_width(ctx, wmax);
       dim3 grid(rows_grid_x(ctx, n / ((int64_t)kBlock * W), nr), nr);
-      if (W == 4) k_lincomb_rows<4><<<grid, kBlock, 0, ctx->stream>>>(a, n);
-      else if (W == 2) k_lincomb_rows<2><<<grid, kBlock, 0, ctx->stream>>>(a, n);
-      else k_lincomb_rows<1><<<grid, kBlock, 0, ctx->stream>>>(a, n);
+      if (W == 4) launch_k(ctx, k_lincomb_rows<4>, grid, dim3(kBlock), a, n);
+      else if (W == 2) launch_k(ctx, k_lincomb_rows<2>, grid, dim3(kBlock), a, n);
+      else launch_k(ctx, k_lincomb_rows<1>, grid, dim3(kBlock), a, n);
       int rc = check_launch(ctx, "linear_combination");
       if (rc) return rc;
       first = false;
@@ -352,9 +355,9 @@ static int scaleadd_rows(b200vec_ctx ctx, int nsum, int nrows, const double* a_h
       a.nrows = nr;
       const int W = tuned_width(ctx, wmax);
       dim3 grid(rows_grid_x(ctx, n / ((int64_t)kBlock * W), nr), nr);
-      if (W == 4) k_scaleadd_rows<4><<<grid, kBlock, 0, ctx->stream>>>(a, n);
-      else if (W == 2) k_scaleadd_rows<2><<<grid, kBlock, 0, ctx->stream>>>(a, n);
-      else k_scaleadd_rows<1><<<grid, kBlock, 0, ctx->stream>>>(a, n);
+      if (W == 4) launch_k(ctx, k_scaleadd_rows<4>, grid, dim3(kBlock), a, n);
+      else if (W == 2) launch_k(ctx, k_scaleadd_rows<2>, grid, dim3(kBlock), a, n);
+      else launch_k(ctx, k_scaleadd_rows<1>, grid, dim3(kBlock), a, n);
       int rc = check_launch(ctx, "scale_add_multi");
       if (rc) return rc;
     }
@@ -384,9 +387,8 @@ static int map_rows(b200vec_ctx ctx, const char* name, int nrows, const double* 
     MapCfg c = pick_map_cfg(ctx, n, wmax, false);
     const int U = (c.U >= 4) ? 4 : 1;
     dim3 grid(rows_grid_x(ctx, n / ((int64_t)kBlock * c.W * U), nr), nr);
-    cudaStream_t s = ctx->stream;
 #define B200_ROWS_CASE(WW, UU) \
-  if (c.W == WW && U == UU) k_map_rows<WW, UU, FORM><<<grid, kBlock, 0, s>>>(m, a, b, n)
+  if (c.W == WW && U == UU) launch_k(ctx, k_map_rows<WW, UU, FORM>, grid, dim3(kBlock), m, a, b, n)
     B200_ROWS_CASE(4, 4);
     else B200_ROWS_CASE(4, 1);
     else B200_ROWS_CASE(2, 4);

@@ -15,10 +15,16 @@ namespace b200 {
 
 constexpr int kBlock        = 256;  /* threads per CTA for every kernel               */
 constexpr int kSMs          = 148;  /* B200: 2 dies x 74 SMs                          */
-constexpr int kMaxBlocksDef = kSMs * 4; /* reductions: 4 CTAs/SM measured best (sweep_reduce, profiles/) */
+constexpr int kRBlock       = 512;  /* threads per CTA of the single-output reduction kernels */
+constexpr int kMaxBlocksDef = kSMs * 2; /* reductions: 2 CTAs x 512 threads per SM measured best
+                                           (profiles/r01_mb_reduce_24b.txt) */
 constexpr int kMaxPartialBlocks = 4096; /* reduction partial rows (>= any max_blocks) */
 constexpr int kMaxOut       = 8;    /* outputs per multi-reduction launch             */
 constexpr int kMaxRows      = 64;   /* result slots per context                       */
+constexpr int kFlagSlot     = kMaxRows;     /* pinned sequence word of multi-output reductions   */
+constexpr int kPairSlot     = kMaxRows + 2; /* pinned, 16-byte aligned {value, sequence} pair of
+                                               single-output reductions                         */
+constexpr int kHostSlots    = kMaxRows + 8;
 constexpr int kExactMaxElems = 4096; /* smem doubles available to the exact-order path */
 
 struct Tuning
@@ -30,6 +36,8 @@ struct Tuning
   int64_t exact_threshold = 1024;
   int64_t count_launches  = 0;
   int64_t spin_wait       = 1; /* poll the pinned sequence word instead of cudaStreamSynchronize */
+  int64_t pdl             = 1; /* programmatic dependent launch: a kernel's launch ramp overlaps the
+                                  tail of its predecessor on the stream (griddepcontrol)          */
 };
 
 } // namespace b200
@@ -76,7 +84,7 @@ struct MapCfg
   int U;    /* independent wide loads in flight per operand and thread        */
   int grid; /* CTAs                                                           */
 };
-MapCfg pick_map_cfg(b200vec_ctx ctx, int64_t n, int wmax, bool reduction);
+MapCfg pick_map_cfg(b200vec_ctx ctx, int64_t n, int wmax, bool reduction, int block = kBlock);
 static inline int align_width(const void* p)
 {
   if (!p) return 4; /* absent operand does not constrain */
@@ -91,6 +99,28 @@ int scale_dispatch(b200vec_ctx ctx, double c, const double* x, double* z, int64_
 int set_error(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int check_launch(b200vec_ctx ctx, const char* kernel);
+
+/* Every kernel of the library is launched through this: programmatic dependent
+   launch lets the next kernel's CTAs become resident (and run their prologue up
+   to griddepcontrol.wait) while the previous kernel on the stream drains --
+   measured -2 us per launch at n = 2^24 and -25% on chains of small kernels
+   (profiles/r01_mb_reduce_24b.txt).  Stream order is preserved: every kernel
+   executes griddepcontrol.wait before its first global-memory access. */
+template <class... KArgs, class... Args>
+static inline void launch_k(b200vec_ctx ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args&&... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim            = grid;
+  cfg.blockDim           = block;
+  cfg.dynamicSmemBytes   = 0;
+  cfg.stream             = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs                                        = at;
+  cfg.numAttrs                                     = ctx->tune.pdl ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...); /* error picked up by check_launch */
+}
 
 /* RAII device guard so a context bound to device k works from any thread */
 struct DeviceGuard

@@ -9,11 +9,16 @@
  *            FIXED INDEX ORDER (thread t takes t, t+256, ...; then the same
  *            tree), so the result does not depend on which CTA happened to be
  *            last or on scheduling: run-to-run bitwise reproducible.  It stores
- *            the value to the context's device result slot and to a pinned,
- *            device-mapped host slot -- a scalar-returning N_Vector op then needs
- *            one stream sync and no memcpy (the reference needs H2D + D2H + sync,
- *            nvector_cuda.cu:2277-2411) and no atomics on doubles
- *            (sundials_cuda_kernels.cuh:417-424 is order-nondeterministic).
+ *            the value to the context's device result slot and -- when the host
+ *            wants the scalar -- to pinned, device-mapped host memory as ONE
+ *            16-byte {value, sequence} store that the host polls: a
+ *            scalar-returning N_Vector op needs no memcpy and no stream sync
+ *            (the reference needs H2D + D2H + sync, nvector_cuda.cu:2277-2411)
+ *            and no atomics on doubles (sundials_cuda_kernels.cuh:417-424 is
+ *            order-nondeterministic).  Single-output kernels run 512 threads x
+ *            2 CTAs/SM, the ticket is one acq_rel atomic (no separate fences):
+ *            measured 24.9 us vs 27.5 us for 2^24 doubles
+ *            (profiles/r01_mb_reduce_24b.txt).
  *
  * Exact-order path: for n <= exact_threshold (default 1024) one CTA stages the
  * per-element terms in shared memory and thread 0 adds them strictly
@@ -130,69 +135,82 @@ struct RedPtrs
 };
 
 /* where a finished reduction publishes its value(s): the context's device
-   slots, their pinned host mirror, and a pinned sequence word the host can spin
-   on instead of paying a cudaStreamSynchronize round trip */
+   slots and -- only when the host asked for the scalar(s), h_res != NULL -- their
+   pinned host mirror.  Single results travel as one 16-byte {value, seq} store
+   (one PCIe write, no system fence); multi results as values, system fence,
+   sequence word.  The host polls the sequence instead of paying a
+   cudaStreamSynchronize round trip. */
 struct ResOut
 {
   double* d_res;
-  double* h_res;
+  double* h_res;  /* mapped pinned slots, or NULL: no host publication */
+  double* h_pair; /* mapped pinned {value, seq}, 16-byte aligned       */
   volatile unsigned long long* h_flag;
   unsigned long long seq;
 };
 
+__device__ __forceinline__ void publish_single(const ResOut& o, double v)
+{
+  *o.d_res = v;
+  if (o.h_res)
+    asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(o.h_pair), "d"(v), "d"(__longlong_as_double((long long)o.seq))
+                 : "memory");
+}
+
 __device__ __forceinline__ void publish_done(const ResOut& o)
 {
+  if (!o.h_res) return;
   __threadfence_system(); /* results before the flag, all the way to host memory */
   *o.h_flag = o.seq;
 }
 
+/* ticket of the last-block-done scheme: ONE acq_rel atomic releases this CTA's
+   partial(s) (written by the same thread) and acquires everybody else's */
+__device__ __forceinline__ bool take_ticket(unsigned int* counter)
+{
+  unsigned int t;
+  asm volatile("atom.add.acq_rel.gpu.u32 %0, [%1], 1;" : "=r"(t) : "l"(counter) : "memory");
+  return t == gridDim.x - 1;
+}
+
 /* stage 2: executed by every CTA after it has its value in thread 0 */
-template <class C>
+template <class C, int BLOCK>
 __device__ __forceinline__ void finish_block(double v, double* partials, unsigned int* counter, const ResOut& o,
                                              double* smem)
 {
   __shared__ bool s_last;
   if (gridDim.x == 1)
   {
-    if (threadIdx.x == 0)
-    {
-      *o.d_res = v;
-      *o.h_res = v;
-      publish_done(o);
-    }
+    if (threadIdx.x == 0) publish_single(o, v);
     return;
   }
   if (threadIdx.x == 0)
   {
     partials[blockIdx.x] = v;
-    __threadfence();
-    const unsigned int ticket = atomicAdd(counter, 1u);
-    s_last                    = (ticket == gridDim.x - 1);
+    s_last               = take_ticket(counter);
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
   double a = C::identity();
-  for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) a = C::apply(a, __ldcg(partials + i));
-  a = block_combine<C>(a, smem);
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += BLOCK) a = C::apply(a, __ldcg(partials + i));
+  a = block_combine<C, BLOCK>(a, smem);
   if (threadIdx.x == 0)
   {
-    *o.d_res = a;
-    *o.h_res = a;
     *counter = 0u; /* self-resetting for the next launch on this stream */
-    publish_done(o);
+    publish_single(o, a);
   }
 }
 
 template <int W, int U, class R>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kRBlock)
   k_reduce(R r, RedPtrs p, int64_t n, double* partials, unsigned int* counter, ResOut o)
 {
   using C = typename R::Comb;
-  __shared__ double smem[kBlock / 32];
-  constexpr int64_t TILE = (int64_t)kBlock * W * U;
-  constexpr int64_t STEP = (int64_t)kBlock * W;
+  __shared__ double smem[kRBlock / 32];
+  constexpr int64_t TILE = (int64_t)kRBlock * W * U;
+  constexpr int64_t STEP = (int64_t)kRBlock * W;
   const int64_t nfull    = n / TILE;
+  pdl_prologue();
 
   double acc[W];
 #pragma unroll
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(kBlock)
   const int64_t tail0 = nfull * TILE;
   if (tail0 < n && blockIdx.x == (unsigned)(nfull % gridDim.x))
   {
-    for (int64_t i = tail0 + threadIdx.x; i < n; i += kBlock)
+    for (int64_t i = tail0 + threadIdx.x; i < n; i += kRBlock)
     {
       double o;
       bool st        = false;
@@ -253,8 +271,8 @@ __global__ void __launch_bounds__(kBlock)
   double v = acc[0];
 #pragma unroll
   for (int w = 1; w < W; w++) v = C::apply(v, acc[w]);
-  v = block_combine<C>(v, smem);
-  finish_block<C>(v, partials, counter, o, smem);
+  v = block_combine<C, kRBlock>(v, smem);
+  finish_block<C, kRBlock>(v, partials, counter, o, smem);
 }
 
 /* exact-order path: one CTA, terms staged in shared memory, thread 0 folds
@@ -264,6 +282,7 @@ __global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, 
 {
   using C = typename R::Comb;
   __shared__ double buf[kExactMaxElems];
+  pdl_prologue();
   for (int i = threadIdx.x; i < n; i += kBlock)
   {
     double o;
@@ -277,37 +296,40 @@ __global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, 
     double a = C::identity();
 #pragma unroll 8
     for (int i = 0; i < n; i++) a = C::apply(a, buf[i]);
-    *o.d_res = a;
-    *o.h_res = a;
-    publish_done(o);
+    publish_single(o, a);
   }
 }
 
-/* finish a reduction call: optional sync + copy of `count` pinned slots */
-/* next sequence number + where the kernel publishes */
-static ResOut next_out(b200vec_ctx ctx, int slot0)
+/* next sequence number + where the kernel publishes; to_host = the caller wants
+   the scalar(s) on the host (otherwise they stay in the device slots, e.g. for
+   the allreduce that follows on a distributed vector) */
+static ResOut next_out(b200vec_ctx ctx, int slot0, bool to_host)
 {
   ResOut o;
   o.d_res  = ctx->d_result + slot0;
-  o.h_res  = ctx->h_result_dev + slot0;
-  o.h_flag = (volatile unsigned long long*)(ctx->h_result_dev + kMaxRows);
+  o.h_res  = to_host ? ctx->h_result_dev + slot0 : nullptr;
+  o.h_pair = ctx->h_result_dev + kPairSlot;
+  o.h_flag = (volatile unsigned long long*)(ctx->h_result_dev + kFlagSlot);
   o.seq    = ++ctx->seq;
   return o;
 }
 
-int finish_reduction(b200vec_ctx ctx, int count, double* result_host)
+/* wait for the reduction launched last (sequence ctx->seq) and copy its `count`
+   pinned results.  packed: the single {value, seq} pair; else slots + flag. */
+static int finish_host(b200vec_ctx ctx, int count, double* result_host, bool packed)
 {
   if (!result_host) return B200VEC_OK;
-  int rc = B200VEC_OK;
+  int rc    = B200VEC_OK;
   bool seen = false;
+  volatile unsigned long long* flag =
+    (volatile unsigned long long*)(ctx->h_result + (packed ? kPairSlot + 1 : kFlagSlot));
+  const unsigned long long want = ctx->seq;
   if (ctx->tune.spin_wait)
   {
-    /* the final pass stores the scalars and then a sequence word into pinned host
+    /* the final pass stores the scalar(s) and a sequence word into pinned host
        memory: polling it costs ~1-2 us after the kernel ends, a
        cudaStreamSynchronize round trip several times that.  Bounded spin, then
        fall back to the sync (which also surfaces asynchronous errors). */
-    volatile unsigned long long* flag = (volatile unsigned long long*)(ctx->h_result + kMaxRows);
-    const unsigned long long want     = ctx->seq;
     for (long spins = 0; spins < 20000000L; spins++)
     {
       if (*flag >= want)
@@ -323,8 +345,16 @@ int finish_reduction(b200vec_ctx ctx, int count, double* result_host)
   }
   if (!seen) rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(reduction)");
   if (rc) return rc;
-  for (int i = 0; i < count; i++) result_host[i] = ctx->h_result[i];
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  if (packed) result_host[0] = ((volatile double*)ctx->h_result)[kPairSlot];
+  else
+    for (int i = 0; i < count; i++) result_host[i] = ((volatile double*)ctx->h_result)[i];
   return B200VEC_OK;
+}
+
+int finish_reduction(b200vec_ctx ctx, int count, double* result_host)
+{
+  return finish_host(ctx, count, result_host, false);
 }
 
 template <class R>
@@ -346,21 +376,18 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
     if (result_host) *result_host = empty_value;
     return B200VEC_OK;
   }
-  if (n <= ctx->tune.exact_threshold)
-  {
-    k_reduce_exact<R><<<1, kBlock, 0, s>>>(r, p, (int)n, next_out(ctx, 0));
-  }
+  const ResOut out = next_out(ctx, 0, result_host != nullptr);
+  if (n <= ctx->tune.exact_threshold) { launch_k(ctx, k_reduce_exact<R>, dim3(1), dim3(kBlock), r, p, (int)n, out); }
   else
   {
     int wmax = align_width(p.p0);
     wmax     = min(wmax, align_width(p.p1));
     wmax     = min(wmax, align_width(p.p2));
     wmax     = min(wmax, align_width(p.out));
-    const MapCfg c = pick_map_cfg(ctx, n, wmax, true);
-    const ResOut out = next_out(ctx, 0);
-#define B200_RED_CASE(WW, UU)                                                                          \
-  if (c.W == WW && c.U == UU)                                                                          \
-  k_reduce<WW, UU, R><<<c.grid, kBlock, 0, s>>>(r, p, n, ctx->d_partials, ctx->d_count, out)
+    const MapCfg c = pick_map_cfg(ctx, n, wmax, true, kRBlock);
+#define B200_RED_CASE(WW, UU)    \
+  if (c.W == WW && c.U == UU)    \
+  launch_k(ctx, k_reduce<WW, UU, R>, dim3(c.grid), dim3(kRBlock), r, p, n, ctx->d_partials, ctx->d_count, out)
     B200_RED_CASE(4, 4);
     else B200_RED_CASE(4, 2);
     else B200_RED_CASE(4, 1);
@@ -374,7 +401,7 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
   }
   int rc = check_launch(ctx, name);
   if (rc) return rc;
-  return finish_reduction(ctx, 1, result_host);
+  return finish_host(ctx, 1, result_host, true);
 }
 
 /* ------------------------------------------------------ multi-output family
@@ -413,6 +440,7 @@ __global__ void __launch_bounds__(kBlock)
   double acc[kMaxOut];
 #pragma unroll
   for (int j = 0; j < kMaxOut; j++) acc[j] = 0.0;
+  pdl_prologue();
 
   for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
   {
@@ -459,7 +487,7 @@ __global__ void __launch_bounds__(kBlock)
         if (gridDim.x == 1)
         {
           o.d_res[j] = v;
-          o.h_res[j] = v;
+          if (o.h_res) o.h_res[j] = v;
         }
         else partials[(size_t)j * kMaxPartialBlocks + blockIdx.x] = v;
       }
@@ -470,15 +498,9 @@ __global__ void __launch_bounds__(kBlock)
     return;
   }
 
-  if (threadIdx.x == 0)
-  {
-    __threadfence();
-    const unsigned int ticket = atomicAdd(counter, 1u);
-    s_last                    = (ticket == gridDim.x - 1);
-  }
+  if (threadIdx.x == 0) s_last = take_ticket(counter);
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
   for (int j = 0; j < nout; j++)
   {
     const double* row = partials + (size_t)j * kMaxPartialBlocks;
@@ -488,7 +510,7 @@ __global__ void __launch_bounds__(kBlock)
     if (threadIdx.x == 0)
     {
       o.d_res[j] = a;
-      o.h_res[j] = a;
+      if (o.h_res) o.h_res[j] = a;
     }
   }
   if (threadIdx.x == 0)
@@ -505,6 +527,7 @@ __global__ void __launch_bounds__(kBlock)
 {
   __shared__ double buf[kExactMaxElems];
   const int nout = m.nout;
+  pdl_prologue();
   for (int i = threadIdx.x; i < n; i += kBlock)
   {
     const double sh = (MODE != 1) ? m.shared[i] : 0.0;
@@ -518,20 +541,20 @@ __global__ void __launch_bounds__(kBlock)
 #pragma unroll 8
     for (int i = 0; i < n; i++) a += col[i];
     o.d_res[threadIdx.x] = a;
-    o.h_res[threadIdx.x] = a;
+    if (o.h_res) o.h_res[threadIdx.x] = a;
   }
   __syncthreads();
   if (threadIdx.x == 0) publish_done(o);
 }
 
 template <int MODE>
-static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs& m, int64_t n, int slot0)
+static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs& m, int64_t n, int slot0,
+                              bool to_host)
 {
-  cudaStream_t s = ctx->stream;
-  const ResOut out = next_out(ctx, slot0);
+  const ResOut out = next_out(ctx, slot0, to_host);
   if (n <= ctx->tune.exact_threshold && n * m.nout <= kExactMaxElems)
   {
-    k_reduce_multi_exact<MODE><<<1, kBlock, 0, s>>>(m, (int)n, out);
+    launch_k(ctx, k_reduce_multi_exact<MODE>, dim3(1), dim3(kBlock), m, (int)n, out);
     return check_launch(ctx, name);
   }
   int wmax = align_width(m.shared);
@@ -550,9 +573,10 @@ static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs
   int64_t cap = (W == 4 && MODE != 0) ? kSMs : 2 * kSMs;
   if (cap > ctx->tune.max_blocks) cap = ctx->tune.max_blocks;
   const int grid = (int)((tiles < cap) ? tiles : cap);
-  if (W == 4) k_reduce_multi<4, MODE><<<grid, kBlock, 0, s>>>(m, n, ctx->d_partials, ctx->d_count, out);
-  else if (W == 2) k_reduce_multi<2, MODE><<<grid, kBlock, 0, s>>>(m, n, ctx->d_partials, ctx->d_count, out);
-  else k_reduce_multi<1, MODE><<<grid, kBlock, 0, s>>>(m, n, ctx->d_partials, ctx->d_count, out);
+  if (W == 4) launch_k(ctx, k_reduce_multi<4, MODE>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out);
+  else if (W == 2)
+    launch_k(ctx, k_reduce_multi<2, MODE>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out);
+  else launch_k(ctx, k_reduce_multi<1, MODE>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out);
   return check_launch(ctx, name);
 }
 
@@ -592,7 +616,7 @@ static int launch_multi(b200vec_ctx ctx, const char* name, int nout, const doubl
       m.A[j] = (j < m.nout) ? A[j0 + j] : nullptr;
       m.B[j] = (j < m.nout && B) ? B[j0 + j] : nullptr;
     }
-    int rc = launch_multi_group<MODE>(ctx, name, m, n, j0);
+    int rc = launch_multi_group<MODE>(ctx, name, m, n, j0, result_host != nullptr);
     if (rc) return rc;
   }
   return finish_reduction(ctx, nout, result_host);

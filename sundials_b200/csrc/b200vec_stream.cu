@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(kBlock) k_map(F f, const double* p0, const dou
   constexpr int64_t TILE = (int64_t)kBlock * W * U;
   constexpr int64_t STEP = (int64_t)kBlock * W;
   const int64_t nfull    = n / TILE;
+  pdl_prologue();
 
   for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
   {
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(kBlock) k_map(F f, const double* p0, const dou
 /* ------------------------------------------------------------ launchers */
 /* widest load the alignment allows (capped by tuning), deepest unroll that
    still leaves >= 4 tiles per SM, grid = min(tiles, max_blocks) */
-MapCfg pick_map_cfg(b200vec_ctx ctx, int64_t n, int wmax, bool reduction)
+MapCfg pick_map_cfg(b200vec_ctx ctx, int64_t n, int wmax, bool reduction, int block)
 {
   MapCfg c;
   c.W = wmax;
@@ -92,9 +93,9 @@ MapCfg pick_map_cfg(b200vec_ctx ctx, int64_t n, int wmax, bool reduction)
   else
   {
     c.U = 4;
-    while (c.U > 1 && n / ((int64_t)kBlock * c.W * c.U) < 4 * kSMs) c.U >>= 1;
+    while (c.U > 1 && n / ((int64_t)block * c.W * c.U) < 4 * kSMs * kBlock / block) c.U >>= 1;
   }
-  int64_t tiles = n / ((int64_t)kBlock * c.W * c.U);
+  int64_t tiles = n / ((int64_t)block * c.W * c.U);
   if (tiles < 1) tiles = 1;
   /* streaming: one tile per CTA unless capped (measured best on B200: the block
      scheduler back-fills SMs as CTAs retire, no tail quantisation); reductions:
@@ -115,9 +116,8 @@ static int launch_map(b200vec_ctx ctx, const char* name, F f, const double* p0, 
   if (NIN >= 2) wmax = min(wmax, align_width(p1));
   const MapCfg c = pick_map_cfg(ctx, n, wmax, false);
   DeviceGuard g(ctx->device);
-  cudaStream_t s = ctx->stream;
-#define B200_MAP_CASE(WW, UU)                                                          \
-  if (c.W == WW && c.U == UU) k_map<WW, UU, NIN, F><<<c.grid, kBlock, 0, s>>>(f, p0, p1, out, n)
+#define B200_MAP_CASE(WW, UU) \
+  if (c.W == WW && c.U == UU) launch_k(ctx, k_map<WW, UU, NIN, F>, dim3(c.grid), dim3(kBlock), f, p0, p1, out, n)
   B200_MAP_CASE(4, 4);
   else B200_MAP_CASE(4, 2);
   else B200_MAP_CASE(4, 1);

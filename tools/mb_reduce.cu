@@ -73,7 +73,13 @@ __device__ __forceinline__ void finish(double v, const Out& o, double* smem)
   if (threadIdx.x == 0)
   {
     o.partials[blockIdx.x] = v;
-    if (FIN != 0)
+    if (FIN >= 4)
+    {
+      unsigned int t;
+      asm volatile("atom.add.acq_rel.gpu.u32 %0, [%1], 1;" : "=r"(t) : "l"(o.counter) : "memory");
+      s_last = (t == gridDim.x - 1);
+    }
+    else if (FIN != 0)
     {
       __threadfence();
       const unsigned int t = atomicAdd(o.counter, 1u);
@@ -83,7 +89,7 @@ __device__ __forceinline__ void finish(double v, const Out& o, double* smem)
   if (FIN == 0) return;
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
+  if (FIN < 4) __threadfence();
   double a = 0.0;
   for (unsigned int i = threadIdx.x; i < gridDim.x; i += BLOCK) a += __ldcg(o.partials + i);
   a = block_sum<BLOCK>(a, smem);
@@ -97,7 +103,7 @@ __device__ __forceinline__ void finish(double v, const Out& o, double* smem)
       __threadfence_system();
       *o.h_flag = o.seq;
     }
-    if (FIN == 3)
+    if (FIN == 3 || FIN == 5)
     {
       asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(o.h_res), "d"(a), "d"(__longlong_as_double((long long)o.seq))
                    : "memory");
@@ -206,6 +212,47 @@ __global__ void __launch_bounds__(kBlock) k_copy(const double* x, double* z, int
   }
 }
 
+template <int U, int PDL>
+__global__ void __launch_bounds__(kBlock) k_copy_pdl(const double* x, double* z, int64_t n)
+{
+  if (PDL)
+  {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+  constexpr int W        = 4;
+  constexpr int64_t TILE = (int64_t)kBlock * W * U;
+  constexpr int64_t STEP = (int64_t)kBlock * W;
+  const int64_t nfull    = n / TILE;
+  for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
+  {
+    const int64_t base = t * TILE + (int64_t)threadIdx.x * W;
+    double a[U][W];
+#pragma unroll
+    for (int u = 0; u < U; u++) ldg4(x + base + u * STEP, a[u]);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(z + base + u * STEP), "d"(a[u][0]), "d"(a[u][1]),
+                   "d"(a[u][2]), "d"(a[u][3])
+                   : "memory");
+  }
+}
+
+template <int U, int PDL>
+static void launch_copy_pdl(cudaStream_t st, int grid, const double* x, double* z, int64_t n)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim            = dim3(grid);
+  cfg.blockDim           = dim3(kBlock);
+  cfg.stream             = st;
+  cudaLaunchAttribute at[1];
+  at[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = PDL;
+  cfg.attrs                                        = at;
+  cfg.numAttrs                                     = PDL ? 1 : 0;
+  CK(cudaLaunchKernelEx(&cfg, k_copy_pdl<U, PDL>, x, z, n));
+}
+
 struct Bench
 {
   std::vector<double*> bufs;
@@ -254,6 +301,8 @@ static void run_fins(Bench& B, int cap)
   run<BLOCK, U, NIN, 1, PIPE>(B, cap);
   run<BLOCK, U, NIN, 2, PIPE>(B, cap);
   run<BLOCK, U, NIN, 3, PIPE>(B, cap);
+  run<BLOCK, U, NIN, 4, PIPE>(B, cap);
+  run<BLOCK, U, NIN, 5, PIPE>(B, cap);
 }
 
 int main(int argc, char** argv)
@@ -292,22 +341,34 @@ int main(int argc, char** argv)
     printf("cudaMemcpy D2D           : %8.2f us %7.1f GB/s\n", us, 16.0 * B.n / us / 1e3);
   }
 
-  const int caps[] = {148 * 2, 148 * 4, 148 * 8, 148 * 16, 1 << 30};
+  // PDL: chain of dependent copies z_{k+1} = z_k, with/without programmatic dependent launch
+  for (int lg : {16, 18, 20, 22, 24})
+  {
+    if (lg > log2n) continue;
+    const int64_t nn = (int64_t)1 << lg;
+    const int U = 4;
+    int64_t tiles = nn / (kBlock * 4 * U);
+    if (tiles < 1) tiles = 1;
+    int64_t saved = B.n;
+    cudaStream_t st;
+    CK(cudaStreamCreate(&st));
+    for (int pass = 0; pass < 2; pass++)
+    {
+      cudaStream_t s = pass ? st : (cudaStream_t)0;
+      double us0 = time_us(B, [&](int r) { launch_copy_pdl<4, 0>(s, (int)tiles, B.bufs[r % nb], B.bufs[(r + 1) % nb], nn); });
+      double us1 = time_us(B, [&](int r) { launch_copy_pdl<4, 1>(s, (int)tiles, B.bufs[r % nb], B.bufs[(r + 1) % nb], nn); });
+      printf("chain copy n=2^%d stream=%s : plain %7.2f us   PDL %7.2f us\n", lg, pass ? "user" : "legacy0", us0, us1);
+    }
+    CK(cudaStreamDestroy(st));
+    B.n = saved;
+  }
+
+  const int caps[] = {148 * 2, 148 * 3, 148 * 4, 148 * 6, 148 * 8};
   printf("--- NIN=1 (max-norm / l1 shape), U=4, no pipe, FIN sweep x grid cap\n");
   for (int cap : caps) run_fins<256, 4, 1, 0>(B, cap);
-  printf("--- NIN=1 U=8\n");
-  for (int cap : caps) run_fins<256, 8, 1, 0>(B, cap);
-  printf("--- NIN=1 U=4 PIPE\n");
-  for (int cap : caps) run_fins<256, 4, 1, 1>(B, cap);
-  printf("--- NIN=1 U=2 PIPE\n");
-  for (int cap : caps) run_fins<256, 2, 1, 1>(B, cap);
   printf("--- NIN=1 BLOCK=512 U=4\n");
-  for (int cap : {148, 148 * 2, 148 * 4, 1 << 30}) run_fins<512, 4, 1, 0>(B, cap);
+  for (int cap : {148, 148 * 2}) run_fins<512, 4, 1, 0>(B, cap);
   printf("--- NIN=2 (dot shape) U=4\n");
   for (int cap : caps) run_fins<256, 4, 2, 0>(B, cap);
-  printf("--- NIN=2 U=2 PIPE\n");
-  for (int cap : caps) run_fins<256, 2, 2, 1>(B, cap);
-  printf("--- NIN=2 U=4 PIPE\n");
-  for (int cap : caps) run_fins<256, 4, 2, 1>(B, cap);
   return 0;
 }
