@@ -320,7 +320,8 @@ def workload_config(args):
                     f"length 2^{args.log2n} per GPU, nvecs={NVECS}, nsums={NSUMS}, fused ops enabled",
         "length_per_gpu": 1 << args.log2n,
         "nvecs": NVECS, "nsums": NSUMS,
-        "partition": "contiguous 1-D block per GPU (MPIPlusX pattern), NCCL allreduce for reductions only",
+        "partition": "contiguous 1-D block per GPU (MPIPlusX pattern); reductions fold the ranks' partials over "
+                     "NVLink peer memory inside the reduction kernel (NCCL allreduce as fallback); no other communication",
         "cache": "inputs larger than L2: every op streams >= 128 MiB per operand (126 MB L2), "
                  "91 distinct vectors (11.4 GiB) rotate through the suite",
     }
@@ -341,12 +342,21 @@ def b200_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything native libraries print there
+    # (e.g. NCCL's version banner) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        import datetime
+
+        # a mismatched collective must fail in minutes, not hold the GPUs for the default 10
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"),
+                                timeout=datetime.timedelta(seconds=180))
 
     lib = _lib.load()
     P = B200Plugin()
@@ -445,13 +455,8 @@ def b200_arm(args):
     value = world * bytes_per_step / (ms_step * 1e-3) / 1e9
     e2e_value = world * bytes_per_step / (ms_e2e * 1e-3) / 1e9
 
-    if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return 0
-
-    # ---- per-op kernel timings (rank 0): each op alone, CUDA events, operands rotate
+    # ---- per-op timings: each op alone, CUDA events.  EVERY rank runs this loop --
+    # the reducing ops of a distributed vector are collectives (SPMD) -- rank 0 reports
     per_op = {}
     peaks = {}
     pk = ROOT / "MEASURED_PEAKS.json"
@@ -538,6 +543,12 @@ def b200_arm(args):
         except Exception:
             pass
 
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -551,11 +562,14 @@ def b200_arm(args):
             cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "reference",
                    "sample": f"unavailable: {e}"}
 
+    cfg = workload_config(args)
+    lib.b200vec_comm_transport.restype = C.c_char_p
+    cfg["reduction_transport"] = lib.b200vec_comm_transport(ctx).decode()
     line = {
         "metric": "N_Vector op suite throughput (algorithmic GB/s)", "value": round(value, 1), "unit": "GB/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args),
+        "config": cfg,
         "e2e": {"value": round(e2e_value, 1), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e, 4)},
         "gpu_launches": launches,
@@ -566,7 +580,8 @@ def b200_arm(args):
         "result_checksum": result_value,
         "ops_per_step": len(suite),
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

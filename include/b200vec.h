@@ -70,6 +70,8 @@ int b200vec_ctx_sync(b200vec_ctx ctx); /* cudaStreamSynchronize on the ctx strea
 /* tuning knobs (sweepable from the bench without recompiling):
  *  "max_blocks"      grid cap of the reduction kernels (default 148*2 CTAs of 512 threads)
  *  "pdl"             1 (default): programmatic dependent launch on every kernel
+ *  "p2p"             1 (default): global reductions exchange over NVLink peer memory
+ *                    inside the reduction kernel; 0: ncclAllReduce (same on all ranks!)
  *  "spin_wait"       1 (default): scalar-returning ops poll a pinned sequence word
  *                    written by the kernel's final pass; 0: cudaStreamSynchronize
  *  "stream_max_blocks" grid cap of streaming/fused kernels (default 0 = one tile per CTA)
@@ -205,10 +207,30 @@ int b200vec_linear_combination_vector_array(b200vec_ctx ctx, int nvec, int nsum,
  * src/nvector/manyvector/nvector_manyvector.c:815-1793).  NCCL is loaded with
  * dlopen("libnccl.so.2") -- no link-time dependency.
  * ---------------------------------------------------------------------- */
+/* reduction scope (one-shot): after b200vec_ctx_set_scope(ctx, B200VEC_SCOPE_GLOBAL)
+ * the NEXT reduction call on the context returns the result over ALL ranks of the
+ * communicator (SUM / MAX / MIN as the op implies, manyvector.c:815,869,1107):
+ * over peer memory the exchange happens inside the reduction kernel's last CTA,
+ * otherwise as ncclAllReduce after it.  Every rank must make the same sequence of
+ * global reductions (SPMD, as with MPI).  The scope falls back to LOCAL after
+ * each reduction call. */
+#define B200VEC_SCOPE_LOCAL  0
+#define B200VEC_SCOPE_GLOBAL 1
+int b200vec_ctx_set_scope(b200vec_ctx ctx, int scope);
+/* "none" (single rank), "peer-memory" or "nccl" */
+const char* b200vec_comm_transport(b200vec_ctx ctx);
+
 #define B200VEC_UNIQUE_ID_BYTES 128
 int b200vec_comm_get_unique_id(unsigned char id[B200VEC_UNIQUE_ID_BYTES]);   /* rank 0, then broadcast */
 int b200vec_comm_init(b200vec_ctx ctx, const unsigned char id[B200VEC_UNIQUE_ID_BYTES], int rank, int nranks);
 int b200vec_comm_finalize(b200vec_ctx ctx);
+/* symmetric peer allocation (collective over the communicator, <= 8 ranks):
+ * every rank allocates `bytes` of zeroed HBM and maps all peers' allocations
+ * through CUDA IPC; ptrs[r] (array of comm_size entries) is rank r's buffer as
+ * addressable from this process -- loads/stores to it travel over NVLink.
+ * Used by the reductions' mailboxes and by applications for halo exchange. */
+int b200vec_comm_peer_alloc(b200vec_ctx ctx, size_t bytes, void** ptrs);
+int b200vec_comm_peer_free(b200vec_ctx ctx, void** ptrs);
 int b200vec_comm_rank(b200vec_ctx ctx);
 int b200vec_comm_size(b200vec_ctx ctx);   /* 1 when no communicator is attached */
 /* in-place allreduce of result slots [0,count) on the ctx stream (no-op when size==1) */

@@ -91,9 +91,13 @@ _SIGS = {
     "b200vec_comm_get_unique_id": (_I, [C.POINTER(C.c_ubyte)]),
     "b200vec_comm_init": (_I, [ctx_t, C.POINTER(C.c_ubyte), _I, _I]),
     "b200vec_comm_finalize": (_I, [ctx_t]),
+    "b200vec_comm_peer_alloc": (_I, [ctx_t, C.c_size_t, C.POINTER(_V)]),
+    "b200vec_comm_peer_free": (_I, [ctx_t, C.POINTER(_V)]),
     "b200vec_comm_rank": (_I, [ctx_t]),
     "b200vec_comm_size": (_I, [ctx_t]),
     "b200vec_allreduce": (_I, [ctx_t, _I, _I]),
+    "b200vec_ctx_set_scope": (_I, [ctx_t, _I]),
+    "b200vec_comm_transport": (C.c_char_p, [ctx_t]),
     "b200vec_allreduce_buffer": (_I, [ctx_t, _V, _I, _I]),
     "b200vec_allreduce_i64_host": (_I, [ctx_t, C.POINTER(C.c_int64), _I]),
 }

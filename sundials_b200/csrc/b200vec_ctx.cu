@@ -199,6 +199,7 @@ int b200vec_ctx_set_tuning(b200vec_ctx ctx, const char* key, int64_t value)
   }
   else if (!strcmp(key, "spin_wait")) ctx->tune.spin_wait = value ? 1 : 0;
   else if (!strcmp(key, "pdl")) ctx->tune.pdl = value ? 1 : 0;
+  else if (!strcmp(key, "p2p")) ctx->tune.p2p = value ? 1 : 0;
   else if (!strcmp(key, "count_launches"))
   {
     ctx->tune.count_launches = value ? 1 : 0;
@@ -219,6 +220,7 @@ int64_t b200vec_ctx_get_tuning(b200vec_ctx ctx, const char* key)
   if (!strcmp(key, "count_launches")) return ctx->tune.count_launches;
   if (!strcmp(key, "spin_wait")) return ctx->tune.spin_wait;
   if (!strcmp(key, "pdl")) return ctx->tune.pdl;
+  if (!strcmp(key, "p2p")) return ctx->tune.p2p;
   return -1;
 }
 

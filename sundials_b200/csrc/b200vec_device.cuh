@@ -74,18 +74,21 @@ __device__ __forceinline__ void pdl_prologue()
  * comparisons, so NaNs never win) rather than fmax/fmin. ---- */
 struct CombSum
 {
+  static constexpr int op = B200VEC_SUM;
   static __device__ __forceinline__ double identity() { return 0.0; }
   static __device__ __forceinline__ double apply(double a, double b) { return a + b; }
   static constexpr bool order_sensitive = true;
 };
 struct CombMax
 {
+  static constexpr int op = B200VEC_MAX;
   static __device__ __forceinline__ double identity() { return 0.0; } /* max |x| starts at 0 (serial:627) */
   static __device__ __forceinline__ double apply(double a, double b) { return (b > a) ? b : a; }
   static constexpr bool order_sensitive = false;
 };
 struct CombMin
 {
+  static constexpr int op = B200VEC_MIN;
   static __device__ __forceinline__ double identity() { return DBL_MAX; }
   static __device__ __forceinline__ double apply(double a, double b) { return (b < a) ? b : a; }
   static constexpr bool order_sensitive = false;
@@ -120,6 +123,53 @@ __device__ __forceinline__ double block_combine(double v, double* smem /* >= BLO
   }
   __syncthreads();
   return r;
+}
+
+/* ---- cross-rank combine over NVLink peer memory (warp-collective).
+ * v: this rank's value, the same in all 32 lanes.  Lane r < nranks posts it into
+ * rank r's mailbox (two tagged 8-byte stores: single-copy atomic, no fence) and
+ * then polls the own mailbox for source r; the values are folded in RANK ORDER
+ * 0,1,.. so every rank computes the bit-identical result (integrators must
+ * branch identically everywhere) and it is independent of arrival order.
+ * Replaces the MPI_Allreduce of nvector_manyvector.c:815-1793 / ncclAllReduce.
+ * A peer that never arrives (dead rank) traps the kernel after ~30 s -- a loud
+ * CUDA error on the host -- instead of hanging the GPU. */
+template <class C>
+__device__ __forceinline__ double xrank_combine_warp(double v, int slot, const XArgs& x)
+{
+  const int lane               = threadIdx.x & 31;
+  const unsigned int par       = x.seq & 1u;
+  const unsigned long long tag = (unsigned long long)x.seq << 32;
+  double vq                    = C::identity();
+  if (lane < x.nranks)
+  {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    unsigned long long* dst = x.mbox[lane] + ((size_t)(par * kMaxPeers + x.rank) * kMaxOut + slot) * 2;
+    const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(w0) : "memory");
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(w1) : "memory");
+
+    const unsigned long long* src = x.mbox[x.rank] + ((size_t)(par * kMaxPeers + lane) * kMaxOut + slot) * 2;
+    unsigned long long a, b, t0 = 0;
+    unsigned int spins = 0;
+    for (;;)
+    {
+      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(a) : "l"(src) : "memory");
+      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(b) : "l"(src + 1) : "memory");
+      if ((a >> 32) == x.seq && (b >> 32) == x.seq) break;
+      if ((++spins & 0xfffu) == 0)
+      {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 30000000000ull) asm volatile("trap;");
+      }
+    }
+    vq = __longlong_as_double((long long)((b << 32) | (a & 0xffffffffull)));
+  }
+  double acc = __shfl_sync(0xffffffffu, vq, 0);
+  for (int q = 1; q < x.nranks; q++) acc = C::apply(acc, __shfl_sync(0xffffffffu, vq, q));
+  return acc;
 }
 
 } // namespace b200

@@ -36,13 +36,32 @@ struct Tuning
   int64_t exact_threshold = 1024;
   int64_t count_launches  = 0;
   int64_t spin_wait       = 1; /* poll the pinned sequence word instead of cudaStreamSynchronize */
+  int64_t p2p             = 1; /* global reductions exchange partials over NVLink peer memory inside
+                                  the reduction kernel (0: ncclAllReduce after the kernel)         */
   int64_t pdl             = 1; /* programmatic dependent launch: a kernel's launch ramp overlaps the
                                   tail of its predecessor on the stream (griddepcontrol)          */
 };
 
 } // namespace b200
 
-struct NcclApi; /* b200vec_comm.cu */
+namespace b200 {
+/* cross-rank exchange over NVLink peer memory (b200vec_comm.cu sets it up, the
+   reduction kernels' epilogue uses it).  Every rank owns a 2 KiB mailbox in its
+   HBM, mapped into every peer through CUDA IPC:
+     word[((parity*kMaxPeers + src)*kMaxOut + slot)*2 + half] = (seq << 32) | 32 bits of the value
+   so each 8-byte store carries its own sequence tag (NCCL-LL style): no fence,
+   no separate flag, one NVLink hop.  Two parities make reuse safe (a rank can be
+   at most one collective ahead of any peer). */
+constexpr int kMaxPeers     = 8;
+constexpr size_t kMboxWords = (size_t)2 * kMaxPeers * kMaxOut * 2;
+struct XArgs
+{
+  unsigned long long* mbox[kMaxPeers]; /* mbox[r]: rank r's mailbox as mapped in this process */
+  int nranks;                          /* 1 = local reduction, no exchange                    */
+  int rank;
+  unsigned int seq; /* collective sequence number, identical on all ranks (SPMD) */
+};
+} // namespace b200
 
 struct b200vec_ctx_s
 {
@@ -73,6 +92,11 @@ struct b200vec_ctx_s
   int rank        = 0;
   int nranks      = 1;
   double* d_commbuf = nullptr;
+  /* peer-memory transport (NVLink): own mailbox + IPC mappings of the peers' */
+  bool p2p_ready               = false;
+  unsigned long long* mbox[b200::kMaxPeers] = {nullptr};
+  unsigned int xseq            = 0;     /* collectives issued so far (same on all ranks)   */
+  bool scope_global            = false; /* one-shot: the next reduction call is global     */
 };
 
 namespace b200 {
@@ -92,6 +116,11 @@ static inline int align_width(const void* p)
   return (a % 32 == 0) ? 4 : (a % 16 == 0) ? 2 : 1;
 }
 int finish_reduction(b200vec_ctx ctx, int count, double* result_host);
+/* consume the one-shot global scope; fills the exchange arguments when the peer
+   transport carries this reduction.  Returns: 0 local, 1 global via peer memory
+   (x filled), 2 global via ncclAllReduce after the kernel */
+int take_scope(b200vec_ctx ctx, XArgs* x);
+void next_xargs(b200vec_ctx ctx, XArgs* x); /* a further collective of the same call */
 int linear_sum_dispatch(b200vec_ctx ctx, double a, const double* x, double b, const double* y, double* z,
                         bool z_is_x, bool z_is_y, int64_t n);
 int scale_dispatch(b200vec_ctx ctx, double c, const double* x, double* z, int64_t n);

@@ -173,15 +173,30 @@ __device__ __forceinline__ bool take_ticket(unsigned int* counter)
   return t == gridDim.x - 1;
 }
 
+/* local value of this rank (valid in thread 0 of the calling CTA) -> optional
+   cross-rank combine by warp 0 -> publication by thread 0.  Called by all
+   threads of ONE CTA (the last one, or the only one). */
+template <class C>
+__device__ __forceinline__ void combine_and_publish(double a, const ResOut& o, const XArgs& x)
+{
+  if (x.nranks > 1)
+  {
+    if (threadIdx.x >= 32) return;
+    a = __shfl_sync(0xffffffffu, a, 0);
+    a = xrank_combine_warp<C>(a, 0, x);
+  }
+  if (threadIdx.x == 0) publish_single(o, a);
+}
+
 /* stage 2: executed by every CTA after it has its value in thread 0 */
 template <class C, int BLOCK>
 __device__ __forceinline__ void finish_block(double v, double* partials, unsigned int* counter, const ResOut& o,
-                                             double* smem)
+                                             const XArgs& x, double* smem)
 {
   __shared__ bool s_last;
   if (gridDim.x == 1)
   {
-    if (threadIdx.x == 0) publish_single(o, v);
+    combine_and_publish<C>(v, o, x);
     return;
   }
   if (threadIdx.x == 0)
@@ -194,16 +209,13 @@ __device__ __forceinline__ void finish_block(double v, double* partials, unsigne
   double a = C::identity();
   for (unsigned int i = threadIdx.x; i < gridDim.x; i += BLOCK) a = C::apply(a, __ldcg(partials + i));
   a = block_combine<C, BLOCK>(a, smem);
-  if (threadIdx.x == 0)
-  {
-    *counter = 0u; /* self-resetting for the next launch on this stream */
-    publish_single(o, a);
-  }
+  if (threadIdx.x == 0) *counter = 0u; /* self-resetting for the next launch on this stream */
+  combine_and_publish<C>(a, o, x);
 }
 
 template <int W, int U, class R>
 __global__ void __launch_bounds__(kRBlock)
-  k_reduce(R r, RedPtrs p, int64_t n, double* partials, unsigned int* counter, ResOut o)
+  k_reduce(R r, RedPtrs p, int64_t n, double* partials, unsigned int* counter, ResOut o, XArgs x)
 {
   using C = typename R::Comb;
   __shared__ double smem[kRBlock / 32];
@@ -272,13 +284,13 @@ __global__ void __launch_bounds__(kRBlock)
 #pragma unroll
   for (int w = 1; w < W; w++) v = C::apply(v, acc[w]);
   v = block_combine<C, kRBlock>(v, smem);
-  finish_block<C, kRBlock>(v, partials, counter, o, smem);
+  finish_block<C, kRBlock>(v, partials, counter, o, x, smem);
 }
 
 /* exact-order path: one CTA, terms staged in shared memory, thread 0 folds
    them left-to-right exactly as the serial loop does */
 template <class R>
-__global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, ResOut o)
+__global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, ResOut o, XArgs x)
 {
   using C = typename R::Comb;
   __shared__ double buf[kExactMaxElems];
@@ -291,13 +303,13 @@ __global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, 
     if (R::HAS_OUT && st) p.out[i] = o;
   }
   __syncthreads();
+  double a = C::identity();
   if (threadIdx.x == 0)
   {
-    double a = C::identity();
 #pragma unroll 8
     for (int i = 0; i < n; i++) a = C::apply(a, buf[i]);
-    publish_single(o, a);
   }
+  combine_and_publish<C>(a, o, x);
 }
 
 /* next sequence number + where the kernel publishes; to_host = the caller wants
@@ -357,13 +369,25 @@ int finish_reduction(b200vec_ctx ctx, int count, double* result_host)
   return finish_host(ctx, count, result_host, false);
 }
 
+/* global reduction without the peer transport: allreduce the device slots with
+   NCCL on the same stream, then one fetch (nvector_manyvector.c:815 pattern) */
+static int finish_global_nccl(b200vec_ctx ctx, int count, int op, double* result_host)
+{
+  int rc = b200vec_allreduce(ctx, count, op);
+  if (!rc && result_host) rc = b200vec_result_fetch(ctx, count, result_host);
+  return rc;
+}
+
 template <class R>
 static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int64_t n, double empty_value,
                          double* result_host)
 {
+  using C = typename R::Comb;
   DeviceGuard g(ctx->device);
   cudaStream_t s = ctx->stream;
-  if (n == 0)
+  XArgs xa;
+  const int scope = take_scope(ctx, &xa); /* 0 local, 1 global over peer memory, 2 global over NCCL */
+  if (n == 0 && scope == 0)
   {
     /* nothing to read: publish the identity (N_VMin on an empty vector is
        undefined in the reference, serial:715; we return DBL_MAX) */
@@ -376,8 +400,11 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
     if (result_host) *result_host = empty_value;
     return B200VEC_OK;
   }
-  const ResOut out = next_out(ctx, 0, result_host != nullptr);
-  if (n <= ctx->tune.exact_threshold) { launch_k(ctx, k_reduce_exact<R>, dim3(1), dim3(kBlock), r, p, (int)n, out); }
+  /* an empty local block of a distributed vector still takes part: the exact
+     kernel with n == 0 contributes the identity */
+  const bool to_host = (result_host != nullptr) && scope != 2;
+  const ResOut out   = next_out(ctx, 0, to_host);
+  if (n <= ctx->tune.exact_threshold) { launch_k(ctx, k_reduce_exact<R>, dim3(1), dim3(kBlock), r, p, (int)n, out, xa); }
   else
   {
     int wmax = align_width(p.p0);
@@ -387,7 +414,7 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
     const MapCfg c = pick_map_cfg(ctx, n, wmax, true, kRBlock);
 #define B200_RED_CASE(WW, UU)    \
   if (c.W == WW && c.U == UU)    \
-  launch_k(ctx, k_reduce<WW, UU, R>, dim3(c.grid), dim3(kRBlock), r, p, n, ctx->d_partials, ctx->d_count, out)
+  launch_k(ctx, k_reduce<WW, UU, R>, dim3(c.grid), dim3(kRBlock), r, p, n, ctx->d_partials, ctx->d_count, out, xa)
     B200_RED_CASE(4, 4);
     else B200_RED_CASE(4, 2);
     else B200_RED_CASE(4, 1);
@@ -401,6 +428,7 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
   }
   int rc = check_launch(ctx, name);
   if (rc) return rc;
+  if (scope == 2) return finish_global_nccl(ctx, 1, C::op, result_host);
   return finish_host(ctx, 1, result_host, true);
 }
 
@@ -427,11 +455,38 @@ __device__ __forceinline__ double multi_term(double sh, double a, double b)
   return (sh > 0.0) ? p * p : 0.0;
 }
 
+/* s_fin[0..nout): this rank's values (visible to the whole CTA).  Warp j folds
+   output j across ranks (kBlock/32 == kMaxOut warps), then threads j < nout
+   store, thread 0 publishes.  Called by ALL threads of one CTA. */
+__device__ __forceinline__ void multi_combine_and_publish(double* s_fin, int nout, const ResOut& o, const XArgs& x)
+{
+  static_assert(kBlock / 32 >= kMaxOut, "one warp per output");
+  if (x.nranks > 1)
+  {
+    const int warp = threadIdx.x >> 5;
+    if (warp < nout)
+    {
+      const double v = xrank_combine_warp<CombSum>(s_fin[warp], warp, x);
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) s_fin[warp] = v;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < nout)
+  {
+    o.d_res[threadIdx.x] = s_fin[threadIdx.x];
+    if (o.h_res) o.h_res[threadIdx.x] = s_fin[threadIdx.x];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) publish_done(o);
+}
+
 template <int W, int MODE>
-__global__ void __launch_bounds__(kBlock)
-  k_reduce_multi(const __grid_constant__ MultiArgs m, int64_t n, double* partials, unsigned int* counter, ResOut o)
+__global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__ MultiArgs m, int64_t n,
+                                                         double* partials, unsigned int* counter, ResOut o, XArgs x)
 {
   __shared__ double smem[kBlock / 32];
+  __shared__ double s_fin[kMaxOut];
   __shared__ bool s_last;
   constexpr int64_t TILE = (int64_t)kBlock * W;
   const int64_t nfull    = n / TILE;
@@ -484,17 +539,14 @@ __global__ void __launch_bounds__(kBlock)
       const double v = block_combine<CombSum>(acc[j], smem);
       if (threadIdx.x == 0)
       {
-        if (gridDim.x == 1)
-        {
-          o.d_res[j] = v;
-          if (o.h_res) o.h_res[j] = v;
-        }
+        if (gridDim.x == 1) s_fin[j] = v;
         else partials[(size_t)j * kMaxPartialBlocks + blockIdx.x] = v;
       }
     }
   if (gridDim.x == 1)
   {
-    if (threadIdx.x == 0) publish_done(o);
+    __syncthreads();
+    multi_combine_and_publish(s_fin, nout, o, x);
     return;
   }
 
@@ -507,25 +559,20 @@ __global__ void __launch_bounds__(kBlock)
     double a          = 0.0;
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) a += __ldcg(row + i);
     a = block_combine<CombSum>(a, smem);
-    if (threadIdx.x == 0)
-    {
-      o.d_res[j] = a;
-      if (o.h_res) o.h_res[j] = a;
-    }
+    if (threadIdx.x == 0) s_fin[j] = a;
   }
-  if (threadIdx.x == 0)
-  {
-    *counter = 0u;
-    publish_done(o);
-  }
+  if (threadIdx.x == 0) *counter = 0u;
+  __syncthreads();
+  multi_combine_and_publish(s_fin, nout, o, x);
 }
 
 /* exact-order multi: n * nout <= kExactMaxElems; thread j folds column j */
 template <int MODE>
 __global__ void __launch_bounds__(kBlock)
-  k_reduce_multi_exact(const __grid_constant__ MultiArgs m, int n, ResOut o)
+  k_reduce_multi_exact(const __grid_constant__ MultiArgs m, int n, ResOut o, XArgs x)
 {
   __shared__ double buf[kExactMaxElems];
+  __shared__ double s_fin[kMaxOut];
   const int nout = m.nout;
   pdl_prologue();
   for (int i = threadIdx.x; i < n; i += kBlock)
@@ -540,21 +587,20 @@ __global__ void __launch_bounds__(kBlock)
     double a          = 0.0;
 #pragma unroll 8
     for (int i = 0; i < n; i++) a += col[i];
-    o.d_res[threadIdx.x] = a;
-    if (o.h_res) o.h_res[threadIdx.x] = a;
+    s_fin[threadIdx.x] = a;
   }
   __syncthreads();
-  if (threadIdx.x == 0) publish_done(o);
+  multi_combine_and_publish(s_fin, nout, o, x);
 }
 
 template <int MODE>
 static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs& m, int64_t n, int slot0,
-                              bool to_host)
+                              bool to_host, const XArgs& xa)
 {
   const ResOut out = next_out(ctx, slot0, to_host);
   if (n <= ctx->tune.exact_threshold && n * m.nout <= kExactMaxElems)
   {
-    launch_k(ctx, k_reduce_multi_exact<MODE>, dim3(1), dim3(kBlock), m, (int)n, out);
+    launch_k(ctx, k_reduce_multi_exact<MODE>, dim3(1), dim3(kBlock), m, (int)n, out, xa);
     return check_launch(ctx, name);
   }
   int wmax = align_width(m.shared);
@@ -573,10 +619,11 @@ static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs
   int64_t cap = (W == 4 && MODE != 0) ? kSMs : 2 * kSMs;
   if (cap > ctx->tune.max_blocks) cap = ctx->tune.max_blocks;
   const int grid = (int)((tiles < cap) ? tiles : cap);
-  if (W == 4) launch_k(ctx, k_reduce_multi<4, MODE>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out);
+  if (W == 4)
+    launch_k(ctx, k_reduce_multi<4, MODE>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out, xa);
   else if (W == 2)
-    launch_k(ctx, k_reduce_multi<2, MODE>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out);
-  else launch_k(ctx, k_reduce_multi<1, MODE>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out);
+    launch_k(ctx, k_reduce_multi<2, MODE>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out, xa);
+  else launch_k(ctx, k_reduce_multi<1, MODE>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out, xa);
   return check_launch(ctx, name);
 }
 
@@ -588,7 +635,9 @@ static int launch_multi(b200vec_ctx ctx, const char* name, int nout, const doubl
 {
   if (nout > kMaxRows) return set_error(B200VEC_ERR_ARG, "%s: at most %d outputs per call", name, kMaxRows);
   DeviceGuard g(ctx->device);
-  if (n == 0)
+  XArgs xa;
+  const int scope = take_scope(ctx, &xa);
+  if (n == 0 && scope == 0)
   {
     for (int j = 0; j < nout; j++) ctx->h_result[j] = 0.0;
     int rc = check_cuda(cudaMemcpyAsync(ctx->d_result, ctx->h_result, sizeof(double) * nout, cudaMemcpyHostToDevice,
@@ -600,12 +649,13 @@ static int launch_multi(b200vec_ctx ctx, const char* name, int nout, const doubl
     return rc;
   }
   int group = kMaxOut;
-  if (n <= ctx->tune.exact_threshold)
+  if (n > 0 && n <= ctx->tune.exact_threshold)
   {
     int fit = (int)(kExactMaxElems / n);
     if (fit < 1) fit = 1;
     if (fit < group) group = fit;
   }
+  const bool to_host = (result_host != nullptr) && scope != 2;
   for (int j0 = 0; j0 < nout; j0 += group)
   {
     MultiArgs m;
@@ -616,9 +666,11 @@ static int launch_multi(b200vec_ctx ctx, const char* name, int nout, const doubl
       m.A[j] = (j < m.nout) ? A[j0 + j] : nullptr;
       m.B[j] = (j < m.nout && B) ? B[j0 + j] : nullptr;
     }
-    int rc = launch_multi_group<MODE>(ctx, name, m, n, j0, result_host != nullptr);
+    if (j0 > 0 && scope == 1) next_xargs(ctx, &xa); /* every group is its own collective */
+    int rc = launch_multi_group<MODE>(ctx, name, m, n, j0, to_host, xa);
     if (rc) return rc;
   }
+  if (scope == 2) return finish_global_nccl(ctx, nout, B200VEC_SUM, result_host);
   return finish_reduction(ctx, nout, result_host);
 }
 

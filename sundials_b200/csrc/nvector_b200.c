@@ -519,19 +519,15 @@ void N_VCompare_B200(sunrealtype c, N_Vector x, N_Vector z)
 }
 
 /* ----------------------------------------------------------------------
- * reductions.  Local forms return the rank-local value (one stream sync, the
- * kernel has already stored the scalar in pinned host memory).  Global forms
- * on a distributed vector leave the local value on the device, allreduce it on
- * the same stream (ncclAllReduce, 8 bytes) and fetch once --
- * nvector_manyvector.c:754-1400 semantics.
+ * reductions.  Local forms return the rank-local value (the kernel stores the
+ * scalar in pinned host memory; no memcpy, no stream sync).  Global forms on a
+ * distributed vector set the one-shot GLOBAL scope: the same kernel then folds
+ * the ranks' partials over NVLink peer memory in its last CTA (or the library
+ * falls back to ncclAllReduce) -- nvector_manyvector.c:754-1400 semantics,
+ * SUM / MAX / MIN implied by the op.
  * -------------------------------------------------------------------- */
-static sunrealtype finish_global(N_Vector v, int op)
-{
-  double r;
-  CHECK_VOID(b200vec_allreduce(NCTX(v), 1, op));
-  CHECK_VOID(b200vec_result_fetch(NCTX(v), 1, &r));
-  return r;
-}
+#define GLOBAL_SCOPE(v) \
+  do { if (NDIST(v)) CHECK_VOID(b200vec_ctx_set_scope(NCTX(v), B200VEC_SCOPE_GLOBAL)); } while (0)
 
 sunrealtype N_VDotProdLocal_B200(N_Vector x, N_Vector y)
 {
@@ -542,9 +538,10 @@ sunrealtype N_VDotProdLocal_B200(N_Vector x, N_Vector y)
 
 sunrealtype N_VDotProd_B200(N_Vector x, N_Vector y)
 {
-  if (!NDIST(x)) return N_VDotProdLocal_B200(x, y);
-  CHECK_VOID(b200vec_dot_prod(NCTX(x), NDEV(x), NDEV(y), NLEN(x), NULL));
-  return finish_global(x, B200VEC_SUM); /* nvector_manyvector.c:815 */
+  double r;
+  GLOBAL_SCOPE(x); /* nvector_manyvector.c:815 */
+  CHECK_VOID(b200vec_dot_prod(NCTX(x), NDEV(x), NDEV(y), NLEN(x), &r));
+  return r;
 }
 
 sunrealtype N_VMaxNormLocal_B200(N_Vector x)
@@ -556,9 +553,10 @@ sunrealtype N_VMaxNormLocal_B200(N_Vector x)
 
 sunrealtype N_VMaxNorm_B200(N_Vector x)
 {
-  if (!NDIST(x)) return N_VMaxNormLocal_B200(x);
-  CHECK_VOID(b200vec_max_norm(NCTX(x), NDEV(x), NLEN(x), NULL));
-  return finish_global(x, B200VEC_MAX); /* :869 */
+  double r;
+  GLOBAL_SCOPE(x); /* :869 */
+  CHECK_VOID(b200vec_max_norm(NCTX(x), NDEV(x), NLEN(x), &r));
+  return r;
 }
 
 sunrealtype N_VMinLocal_B200(N_Vector x)
@@ -570,9 +568,10 @@ sunrealtype N_VMinLocal_B200(N_Vector x)
 
 sunrealtype N_VMin_B200(N_Vector x)
 {
-  if (!NDIST(x)) return N_VMinLocal_B200(x);
-  CHECK_VOID(b200vec_min(NCTX(x), NDEV(x), NLEN(x), NULL));
-  return finish_global(x, B200VEC_MIN); /* :1107 */
+  double r;
+  GLOBAL_SCOPE(x); /* :1107 */
+  CHECK_VOID(b200vec_min(NCTX(x), NDEV(x), NLEN(x), &r));
+  return r;
 }
 
 sunrealtype N_VL1NormLocal_B200(N_Vector x)
@@ -584,9 +583,10 @@ sunrealtype N_VL1NormLocal_B200(N_Vector x)
 
 sunrealtype N_VL1Norm_B200(N_Vector x)
 {
-  if (!NDIST(x)) return N_VL1NormLocal_B200(x);
-  CHECK_VOID(b200vec_l1_norm(NCTX(x), NDEV(x), NLEN(x), NULL));
-  return finish_global(x, B200VEC_SUM); /* :1203 */
+  double r;
+  GLOBAL_SCOPE(x); /* :1203 */
+  CHECK_VOID(b200vec_l1_norm(NCTX(x), NDEV(x), NLEN(x), &r));
+  return r;
 }
 
 sunrealtype N_VWSqrSumLocal_B200(N_Vector x, N_Vector w)
@@ -605,10 +605,11 @@ sunrealtype N_VWSqrSumMaskLocal_B200(N_Vector x, N_Vector w, N_Vector id)
 
 static sunrealtype wsqr_global(N_Vector x, N_Vector w, N_Vector id)
 {
-  if (!NDIST(x)) return id ? N_VWSqrSumMaskLocal_B200(x, w, id) : N_VWSqrSumLocal_B200(x, w);
-  if (id) CHECK_VOID(b200vec_wsqr_sum_mask(NCTX(x), NDEV(x), NDEV(w), NDEV(id), NLEN(x), NULL));
-  else CHECK_VOID(b200vec_wsqr_sum(NCTX(x), NDEV(x), NDEV(w), NLEN(x), NULL));
-  return finish_global(x, B200VEC_SUM); /* :956, :1050, :1128 */
+  double r;
+  GLOBAL_SCOPE(x); /* :956, :1050, :1128 */
+  if (id) CHECK_VOID(b200vec_wsqr_sum_mask(NCTX(x), NDEV(x), NDEV(w), NDEV(id), NLEN(x), &r));
+  else CHECK_VOID(b200vec_wsqr_sum(NCTX(x), NDEV(x), NDEV(w), NLEN(x), &r));
+  return r;
 }
 
 /* serial:641-648 -- divides by the GLOBAL length (nvector_manyvector.c:963) */
@@ -633,9 +634,10 @@ sunbooleantype N_VInvTestLocal_B200(N_Vector x, N_Vector z)
 
 sunbooleantype N_VInvTest_B200(N_Vector x, N_Vector z)
 {
-  if (!NDIST(x)) return N_VInvTestLocal_B200(x, z);
-  CHECK_VOID(b200vec_inv_test(NCTX(z), NDEV(x), NDEV(z), NLEN(z), NULL));
-  return (finish_global(x, B200VEC_MIN) > 0.5) ? SUNTRUE : SUNFALSE; /* :1277 */
+  double r;
+  GLOBAL_SCOPE(x); /* :1277 */
+  CHECK_VOID(b200vec_inv_test(NCTX(z), NDEV(x), NDEV(z), NLEN(z), &r));
+  return (r > 0.5) ? SUNTRUE : SUNFALSE;
 }
 
 sunbooleantype N_VConstrMaskLocal_B200(N_Vector c, N_Vector x, N_Vector m)
@@ -647,9 +649,10 @@ sunbooleantype N_VConstrMaskLocal_B200(N_Vector c, N_Vector x, N_Vector m)
 
 sunbooleantype N_VConstrMask_B200(N_Vector c, N_Vector x, N_Vector m)
 {
-  if (!NDIST(x)) return N_VConstrMaskLocal_B200(c, x, m);
-  CHECK_VOID(b200vec_constr_mask(NCTX(m), NDEV(c), NDEV(x), NDEV(m), NLEN(m), NULL));
-  return (finish_global(x, B200VEC_MIN) > 0.5) ? SUNTRUE : SUNFALSE; /* :1339 */
+  double r;
+  GLOBAL_SCOPE(x); /* :1339 */
+  CHECK_VOID(b200vec_constr_mask(NCTX(m), NDEV(c), NDEV(x), NDEV(m), NLEN(m), &r));
+  return (r > 0.5) ? SUNTRUE : SUNFALSE;
 }
 
 sunrealtype N_VMinQuotientLocal_B200(N_Vector num, N_Vector denom)
@@ -661,9 +664,10 @@ sunrealtype N_VMinQuotientLocal_B200(N_Vector num, N_Vector denom)
 
 sunrealtype N_VMinQuotient_B200(N_Vector num, N_Vector denom)
 {
-  if (!NDIST(num)) return N_VMinQuotientLocal_B200(num, denom);
-  CHECK_VOID(b200vec_min_quotient(NCTX(num), NDEV(num), NDEV(denom), NLEN(num), NULL));
-  return finish_global(num, B200VEC_MIN); /* :1399 */
+  double r;
+  GLOBAL_SCOPE(num); /* :1399 */
+  CHECK_VOID(b200vec_min_quotient(NCTX(num), NDEV(num), NDEV(denom), NLEN(num), &r));
+  return r;
 }
 
 /* ----------------------------------------------------------------------
@@ -759,11 +763,11 @@ SUNErrCode N_VDotProdMulti_B200(int nvec, N_Vector x, N_Vector* Y, sunrealtype* 
   for (int j0 = 0; j0 < nvec && !rc; j0 += MAX_STACK_VECS)
   {
     int nj = (nvec - j0 < MAX_STACK_VECS) ? nvec - j0 : MAX_STACK_VECS;
-    /* fused local dots, then ONE nj-wide allreduce (nvector_manyvector.c:1576;
-       the reference's local part is nj separate kernels + syncs, :1566-1570) */
-    rc = b200vec_dot_prod_multi(NCTX(x), nj, NDEV(x), ty.p + j0, NLEN(x), NULL);
-    if (!rc) rc = b200vec_allreduce(NCTX(x), nj, B200VEC_SUM);
-    if (!rc) rc = b200vec_result_fetch(NCTX(x), nj, dotprods + j0);
+    /* fused local dots and ONE nj-wide exchange inside the same kernel
+       (nvector_manyvector.c:1576; the reference's local part is nj separate
+       kernels + syncs, :1566-1570) */
+    rc = b200vec_ctx_set_scope(NCTX(x), B200VEC_SCOPE_GLOBAL);
+    if (!rc) rc = b200vec_dot_prod_multi(NCTX(x), nj, NDEV(x), ty.p + j0, NLEN(x), dotprods + j0);
   }
   table_free(&ty);
   return map_err(rc);
@@ -862,9 +866,8 @@ static SUNErrCode wrms_va(int nvec, N_Vector* X, N_Vector* W, N_Vector id, sunre
   for (int j0 = 0; j0 < nvec && !rc; j0 += MAX_STACK_VECS)
   {
     int nj = (nvec - j0 < MAX_STACK_VECS) ? nvec - j0 : MAX_STACK_VECS;
-    rc = b200vec_wsqr_sum_vector_array(ctx, nj, tx.p + j0, tw.p + j0, idd, NLEN(x0), dist ? NULL : nrm + j0);
-    if (!rc && dist) rc = b200vec_allreduce(ctx, nj, B200VEC_SUM); /* nvector_manyvector.c:1749,1793 */
-    if (!rc && dist) rc = b200vec_result_fetch(ctx, nj, nrm + j0);
+    if (dist) rc = b200vec_ctx_set_scope(ctx, B200VEC_SCOPE_GLOBAL); /* nvector_manyvector.c:1749,1793 */
+    if (!rc) rc = b200vec_wsqr_sum_vector_array(ctx, nj, tx.p + j0, tw.p + j0, idd, NLEN(x0), nrm + j0);
   }
   table_free(&tx);
   table_free(&tw);

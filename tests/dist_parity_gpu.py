@@ -33,7 +33,9 @@ from sundials_b200.plugin import B200Plugin  # noqa: E402
 def main():
     rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lrank)
-    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{lrank}"))
+    import datetime
+
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{lrank}"), timeout=datetime.timedelta(seconds=120))
     lib = _lib.load()
     P = B200Plugin()
     orc = Oracle()
@@ -49,7 +51,14 @@ def main():
     assert lib.b200vec_comm_size(ctx) == world and lib.b200vec_comm_rank(ctx) == rank
 
     fails = 0
-    for n in (1000, 3_000_001):
+    # both transports: cross-rank fold inside the reduction kernel over NVLink peer
+    # memory (default), then ncclAllReduce after the kernel ("p2p" = 0 on all ranks)
+    cases = [(p2p, n) for p2p in (1, 0) for n in (1, 1000, 3_000_001)]
+    for p2p, n in cases:
+        _lib.check(lib.b200vec_ctx_set_tuning(ctx, b"p2p", p2p), "set_tuning(p2p)")
+        transport = lib.b200vec_comm_transport(ctx).decode()
+        if rank == 0:
+            print(f"-- n={n} transport={transport}", flush=True)
         rng = np.random.default_rng(4242)          # identical global data on all ranks
         gx, gy = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
         gw = rng.uniform(0.5, 2.0, n)
@@ -60,8 +69,9 @@ def main():
 
         def mk(g):
             v = P.new(nl, ctx, P.DEVICE, fused=True)
-            P.host(v, nl)[...] = g[a:b]
-            P.to_device(v)
+            if nl > 0:      # n=1 on 2+ ranks: some ranks own an EMPTY block and must still take part
+                P.host(v, nl)[...] = g[a:b]
+                P.to_device(v)
             assert lib.N_VMakeDistributed_B200(v, -1) == 0      # global length by allreduce
             return v
 
@@ -100,10 +110,11 @@ def main():
         if bool(P.ConstrMask(cn, x, z)) != want:
             fails += 1
             print(f"[rank {rank}] MISMATCH constrmask")
-        P.from_device(z)
-        if not np.array_equal(P.host(z, nl), zo[a:b]):
-            fails += 1
-            print(f"[rank {rank}] MISMATCH constrmask mask block")
+        if nl > 0:
+            P.from_device(z)
+            if not np.array_equal(P.host(z, nl), zo[a:b]):
+                fails += 1
+                print(f"[rank {rank}] MISMATCH constrmask mask block")
         # fused reductions: ONE nv-wide allreduce
         dots = (C.c_double * 3)()
         assert P.DotProdMulti(3, x, P.varray([y, w, x]), dots) == 0
@@ -127,10 +138,11 @@ def main():
         P.LinearSum(0.3, x, -2.1, y, z)
         zo = np.empty(n)
         orc.linear_sum(0.3, gx, -2.1, gy, zo)
-        P.from_device(z)
-        if not np.array_equal(P.host(z, nl).view(np.uint64), zo[a:b].view(np.uint64)):
-            fails += 1
-            print(f"[rank {rank}] MISMATCH linear_sum block")
+        if nl > 0:
+            P.from_device(z)
+            if not np.array_equal(P.host(z, nl).view(np.uint64), zo[a:b].view(np.uint64)):
+                fails += 1
+                print(f"[rank {rank}] MISMATCH linear_sum block")
         # identical scalars on every rank (integrators must branch identically)
         v = torch.tensor([P.WrmsNorm(x, w)], dtype=torch.float64, device="cuda")
         lst = [torch.zeros_like(v) for _ in range(world)]
