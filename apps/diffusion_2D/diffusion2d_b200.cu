@@ -1,0 +1,703 @@
+/* diffusion2d_b200.cu -- re-host of the reference's benchmarks/diffusion_2D
+ * (ARKODE DIRK + PCG + Jacobi) on NVECTOR_B200, without MPI.
+ *
+ * What the reference does per right-hand-side evaluation (mpi_gpu/diffusion.cpp:341-397):
+ *   pack_buffers kernel -> 4x MPI_Irecv/Isend of device buffers (CUDA-aware MPI) ->
+ *   interior kernel -> MPI_Wait -> boundary kernel, and 6 sin/cos per grid point
+ *   for the forcing term (:38-57).
+ * Here it is ONE kernel (k_diffusion_rhs):
+ *   - 1-D strips in y; each CTA marches R rows of a 1024-point x-tile keeping the
+ *     three stencil rows in registers (each u value is read from HBM once),
+ *     west/east neighbours by warp shuffle;
+ *   - the CTAs that own the strip's first / last row first PUSH that row into the
+ *     neighbour rank's halo buffer over NVLink peer memory (symmetric allocation,
+ *     b200vec_comm_peer_alloc) and bump the neighbour's arrival counter, then
+ *     compute their other rows, and only at the very end wait for the
+ *     neighbour's row and finish the halo-dependent row: exchange and stencil
+ *     overlap inside the kernel, no pack kernel, no host-side wait;
+ *   - the forcing b(t,x,y) is separable: per-x and per-y factor tables (built
+ *     once with the host libm, exactly the factors of mpi_serial/diffusion.cpp:60-90)
+ *     and two per-call time factors give the reference's expression with ~10
+ *     flops per point instead of 6 transcendental calls.
+ * Everything else -- vectors, Krylov dot products, norms, linear combinations --
+ * is NVECTOR_B200 called by the unmodified ARKODE / SUNLinSol_PCG.
+ */
+#include <arkode/arkode_arkstep.h>
+#include <cuda_runtime.h>
+#include <sunlinsol/sunlinsol_pcg.h>
+#include <sunlinsol/sunlinsol_spgmr.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "diffusion2d_b200.h"
+#include "nvector_b200.h"
+
+#define PI_ 3.141592653589793238462643383279502884197169
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct RhsArgs
+{
+  const double* u;
+  double* f;
+  int64_t nx, ny, ny_loc, js;
+  double cx, cy, cc;
+  double stct, c2t; /* sin(pi t) cos(pi t), cos^2(pi t) */
+  int forcing;
+  const double *ax, *dcx, *ssx; /* per x: (-2 pi) sin^2, bx (cos^2 - sin^2), sin^2 */
+  const double *ssy, *dcy;      /* per local y: sin^2, by (cos^2 - sin^2)          */
+  /* halo exchange over peer memory */
+  int hasS, hasN;
+  double* sendS;       /* S neighbour's "row from the north" buffer (this call's parity) */
+  double* sendN;       /* N neighbour's "row from the south" buffer                      */
+  const double* recvS; /* own buffers                                                     */
+  const double* recvN;
+  unsigned long long* ctrS_remote; /* S neighbour's arrivals-from-north counter */
+  unsigned long long* ctrN_remote; /* N neighbour's arrivals-from-south counter */
+  const unsigned long long* ctrS_local;
+  const unsigned long long* ctrN_local;
+  unsigned long long expected; /* call number x x-tiles: counters are cumulative */
+};
+
+template <int W>
+__device__ __forceinline__ void ld_row(const double* p, double (&v)[W])
+{
+  if (W == 4)
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+  else v[0] = *p;
+}
+/* halo rows were written by another GPU: read them at L2 */
+template <int W>
+__device__ __forceinline__ void ld_halo(const double* p, double (&v)[W])
+{
+  if (W == 4)
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+  else asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v[0]) : "l"(p) : "memory");
+}
+template <int W>
+__device__ __forceinline__ void st_row(double* p, const double (&v)[W])
+{
+  if (W == 4)
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+  else *p = v[0];
+}
+
+__device__ __forceinline__ void wait_counter(const unsigned long long* ctr, unsigned long long expected)
+{
+  if (threadIdx.x == 0)
+  {
+    unsigned long long v, t0 = 0;
+    unsigned int spins = 0;
+    for (;;)
+    {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+      if (v >= expected) break;
+      if ((++spins & 0xfffu) == 0)
+      {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 30000000000ull) asm volatile("trap;"); /* dead neighbour: fail loudly, do not hang */
+      }
+    }
+  }
+  __syncthreads();
+}
+
+/* one stencil row: s/c/n = south/centre/north values of this thread's W points */
+template <int W>
+__device__ __forceinline__ void compute_row(const RhsArgs& a, int64_t j, int64_t x0, bool act, const double (&s)[W],
+                                            const double (&c)[W], const double (&n)[W], const double (&tax)[W],
+                                            const double (&tdcx)[W], const double (&tssx)[W])
+{
+  /* west / east neighbours: lanes exchange their edge values, warp edges read memory */
+  const int lane = threadIdx.x & 31;
+  double w = __shfl_up_sync(0xffffffffu, c[W - 1], 1);
+  double e = __shfl_down_sync(0xffffffffu, c[0], 1);
+  if (!act) return;
+  const double* row = a.u + j * a.nx;
+  if (lane == 0 && x0 > 0) w = row[x0 - 1];
+  if (lane == 31 && x0 + W < a.nx) e = row[x0 + W];
+  const int64_t jg   = a.js + j;
+  const bool ybound  = (jg == 0) || (jg == a.ny - 1);
+  double sy = 0.0, dy = 0.0;
+  if (a.forcing && !ybound)
+  {
+    sy = a.ssy[j];
+    dy = a.dcy[j];
+  }
+  double r[W];
+#pragma unroll
+  for (int k = 0; k < W; k++)
+  {
+    const int64_t i = x0 + k;
+    const double uw = (k == 0) ? w : c[k - 1];
+    const double ue = (k == W - 1) ? e : c[k + 1];
+    double v        = 0.0;
+    if (!ybound && i > 0 && i < a.nx - 1)
+    {
+      /* mpi_serial/diffusion.cpp:98-101 / mpi_gpu/diffusion.cpp:83 */
+      v = a.cc * c[k] + a.cx * (uw + ue) + a.cy * (s[k] + n[k]);
+      if (a.forcing)
+      {
+        /* -2 pi sin^2x sin^2y sin t cos t - bx (cos^2x - sin^2x) sin^2y cos^2t
+           - by (cos^2y - sin^2y) sin^2x cos^2t, left to right as the reference writes it */
+        const double b = tax[k] * sy * a.stct - tdcx[k] * sy * a.c2t - dy * tssx[k] * a.c2t;
+        v += b;
+      }
+    }
+    r[k] = v;
+  }
+  st_row<W>(a.f + j * a.nx + x0, r);
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads) k_diffusion_rhs(const __grid_constant__ RhsArgs a, int R)
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int64_t x0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * W;
+  const bool act   = x0 < a.nx;
+  /* row blocks: the two that own the strip's first and last rows are scheduled
+     FIRST so that their pushes leave at kernel start */
+  const int nyb = gridDim.y;
+  int yb        = blockIdx.y;
+  if (nyb > 2) yb = (blockIdx.y == 0) ? 0 : (blockIdx.y == 1) ? nyb - 1 : blockIdx.y - 1;
+  const int64_t jb = (int64_t)yb * R;
+  const int64_t je = (jb + R < a.ny_loc) ? jb + R : a.ny_loc;
+  const bool ownS  = (jb == 0) && a.hasS;
+  const bool ownN  = (je == a.ny_loc) && a.hasN;
+  const int64_t xo = act ? x0 : 0; /* inactive threads read a valid address, results unused */
+
+  /* ---- 1. push the boundary rows to the neighbours */
+  if (ownS || ownN)
+  {
+    double v[W];
+    if (ownS && act)
+    {
+      ld_row<W>(a.u + xo, v);
+      st_row<W>(a.sendS + xo, v);
+    }
+    if (ownN && act)
+    {
+      ld_row<W>(a.u + (a.ny_loc - 1) * a.nx + xo, v);
+      st_row<W>(a.sendN + xo, v);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      if (ownS) atomicAdd_system(a.ctrS_remote, 1ull);
+      if (ownN) atomicAdd_system(a.ctrN_remote, 1ull);
+    }
+  }
+
+  double tax[W], tdcx[W], tssx[W];
+#pragma unroll
+  for (int k = 0; k < W; k++) tax[k] = tdcx[k] = tssx[k] = 0.0;
+  if (a.forcing && act)
+  {
+    ld_row<W>(a.ax + xo, tax);
+    ld_row<W>(a.dcx + xo, tdcx);
+    ld_row<W>(a.ssx + xo, tssx);
+  }
+
+  /* ---- 2. march the rows that need no halo: [m0, m1), two rows of look-ahead */
+  const int64_t m0 = jb + (ownS ? 1 : 0);
+  const int64_t m1 = je - (ownN ? 1 : 0);
+  if (m0 < m1)
+  {
+    double prev[W], cur[W], nxt[W], nxt2[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) prev[k] = cur[k] = nxt[k] = nxt2[k] = 0.0;
+    if (m0 > 0) ld_row<W>(a.u + (m0 - 1) * a.nx + xo, prev);
+    ld_row<W>(a.u + m0 * a.nx + xo, cur);
+    if (m0 + 1 < a.ny_loc) ld_row<W>(a.u + (m0 + 1) * a.nx + xo, nxt);
+    for (int64_t j = m0; j < m1; j++)
+    {
+      if (j + 1 < m1 && j + 2 < a.ny_loc) ld_row<W>(a.u + (j + 2) * a.nx + xo, nxt2);
+      compute_row<W>(a, j, x0, act, prev, cur, nxt, tax, tdcx, tssx);
+#pragma unroll
+      for (int k = 0; k < W; k++)
+      {
+        prev[k] = cur[k];
+        cur[k]  = nxt[k];
+        nxt[k]  = nxt2[k];
+      }
+    }
+  }
+
+  /* ---- 3. the halo-dependent rows, last */
+  if (ownN)
+  {
+    const int64_t j = a.ny_loc - 1;
+    double s[W], c[W], n[W];
+    ld_row<W>(a.u + (j - 1) * a.nx + xo, s);
+    ld_row<W>(a.u + j * a.nx + xo, c);
+    wait_counter(a.ctrN_local, a.expected);
+    ld_halo<W>(a.recvN + xo, n);
+    compute_row<W>(a, j, x0, act, s, c, n, tax, tdcx, tssx);
+  }
+  if (ownS)
+  {
+    double s[W], c[W], n[W];
+    ld_row<W>(a.u + xo, c);
+    ld_row<W>(a.u + a.nx + xo, n);
+    wait_counter(a.ctrS_local, a.expected);
+    ld_halo<W>(a.recvS + xo, s);
+    compute_row<W>(a, 0, x0, act, s, c, n, tax, tdcx, tssx);
+  }
+}
+
+/* u = sin^2(pi x) sin^2(pi y) cos^2(pi t) inside, 0 on the boundary
+   (mpi_serial/solution.cpp:25-62) */
+__global__ void __launch_bounds__(kThreads) k_solution(double* u, int64_t nx, int64_t ny, int64_t ny_loc, int64_t js,
+                                                       const double* ssx, const double* ssy, double c2t)
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int64_t total = nx * ny_loc;
+  for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < total; c += (int64_t)gridDim.x * kThreads)
+  {
+    const int64_t j = c / nx, i = c - j * nx, jg = js + j;
+    const bool inside = (i > 0 && i < nx - 1 && jg > 0 && jg < ny - 1);
+    u[c]              = inside ? ssx[i] * ssy[j] * c2t : 0.0;
+  }
+}
+
+} // namespace
+
+struct b200_diffusion2d_plan_s
+{
+  b200vec_ctx ctx     = nullptr;
+  b200_diffusion2d_opts o;
+  int rank = 0, np = 1;
+  int64_t nx = 0, ny = 0, ny_loc = 0, js = 0, nodes = 0, nodes_loc = 0;
+  double dx = 0, dy = 0;
+  int hasS = 0, hasN = 0;
+  double* d_tables = nullptr; /* ax | dcx | ssx (nx each) | ssy | dcy (ny_loc each) */
+  /* symmetric halo region: [16 u64 counters][Srecv 2 x nx][Nrecv 2 x nx] */
+  void* peers[8]          = {nullptr};
+  bool have_peers         = false;
+  unsigned long long seq  = 0;
+  int tiles_x             = 1;
+  int W                   = 4;
+  N_Vector diag           = nullptr; /* Jacobi */
+  /* timing */
+  bool time_rhs = false;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double rhs_ms = 0;
+  long rhs_calls = 0;
+};
+
+namespace {
+
+inline unsigned long long* ctr_of(void* base, int which) { return (unsigned long long*)base + 8 * which; } /* 0 fromS, 1 fromN */
+inline double* srecv_of(void* base, int64_t nx, int par) { return (double*)((unsigned long long*)base + 16) + (size_t)par * nx; }
+inline double* nrecv_of(void* base, int64_t nx, int par) { return (double*)((unsigned long long*)base + 16) + (size_t)(2 + par) * nx; }
+
+int fail(const char* what)
+{
+  fprintf(stderr, "[diffusion2d_b200] ERROR: %s (%s)\n", what, b200vec_last_error());
+  return -1;
+}
+
+} // namespace
+
+extern "C" {
+
+void b200_diffusion2d_default_opts(b200_diffusion2d_opts* o)
+{
+  memset(o, 0, sizeof(*o));
+  o->nx = o->ny = 32;
+  o->xu = o->yu = 1.0;
+  o->kx = o->ky = 1.0;
+  o->tf         = 1.0;
+  o->forcing    = 1;
+  o->rtol       = 1e-5;
+  o->atol       = 1e-10;
+  o->order      = 3;
+  o->linear     = 1;
+  o->ls_gmres   = 0;
+  o->preconditioning = 1;
+  o->liniters   = 20;
+  o->msbp       = 0;
+  o->epslin     = 0.0;
+  o->maxsteps   = 0;
+  strcpy(o->controller, "I");
+  o->output       = 1;
+  o->nout         = 20;
+  o->fused_ops    = 1;
+  o->rows_per_cta = 32;
+}
+
+int b200_diffusion2d_plan_create(b200vec_ctx ctx, const b200_diffusion2d_opts* opts, b200_diffusion2d_plan* out)
+{
+  if (!ctx || !opts || !out) return -1;
+  auto* p = new b200_diffusion2d_plan_s();
+  p->ctx  = ctx;
+  p->o    = *opts;
+  p->rank = b200vec_comm_rank(ctx);
+  p->np   = b200vec_comm_size(ctx);
+  p->nx   = opts->nx;
+  p->ny   = opts->ny;
+  /* y-extents of this strip: UserData::setup, diffusion_2D.cpp:323-329 with npx = 1, npy = np */
+  const int64_t qy = p->ny / p->np, ry = p->ny % p->np;
+  p->js            = qy * p->rank + (p->rank < ry ? p->rank : ry);
+  p->ny_loc        = qy + (p->rank < ry ? 1 : 0);
+  p->nodes         = p->nx * p->ny;
+  p->nodes_loc     = p->nx * p->ny_loc;
+  p->dx            = opts->xu / (double)(p->nx - 1);
+  p->dy            = opts->yu / (double)(p->ny - 1);
+  p->hasS          = (p->js != 0);
+  p->hasN          = (p->js + p->ny_loc != p->ny);
+  if (p->np > 1 && p->ny_loc < 2)
+  {
+    delete p;
+    return fail("every rank needs at least 2 mesh rows");
+  }
+  p->W       = (p->nx % 4 == 0) ? 4 : 1;
+  p->tiles_x = (int)((p->nx + (int64_t)kThreads * p->W - 1) / ((int64_t)kThreads * p->W));
+  if (p->o.rows_per_cta < 2) p->o.rows_per_cta = 2;
+
+  /* factor tables with the HOST libm: the same factors the reference's CPU
+     code evaluates per point (mpi_serial/diffusion.cpp:60-90) */
+  const int64_t nx = p->nx, nyl = p->ny_loc;
+  std::vector<double> t(3 * nx + 2 * nyl);
+  const double bx = opts->kx * 2.0 * PI_ * PI_, by = opts->ky * 2.0 * PI_ * PI_;
+  for (int64_t i = 0; i < nx; i++)
+  {
+    const double x   = (double)i * p->dx;
+    const double ssx = sin(PI_ * x) * sin(PI_ * x), csx = cos(PI_ * x) * cos(PI_ * x);
+    t[i]             = -2.0 * PI_ * ssx;
+    t[nx + i]        = bx * (csx - ssx);
+    t[2 * nx + i]    = ssx;
+  }
+  for (int64_t j = 0; j < nyl; j++)
+  {
+    const double y   = (double)(p->js + j) * p->dy;
+    const double ssy = sin(PI_ * y) * sin(PI_ * y), csy = cos(PI_ * y) * cos(PI_ * y);
+    t[3 * nx + j]       = ssy;
+    t[3 * nx + nyl + j] = by * (csy - ssy);
+  }
+  void* d = nullptr;
+  if (b200vec_malloc_device(ctx, t.size() * sizeof(double), &d)) { delete p; return fail("table allocation"); }
+  p->d_tables = (double*)d;
+  if (b200vec_copy_h2d(ctx, d, t.data(), t.size() * sizeof(double), 1)) { delete p; return fail("table upload"); }
+
+  if (p->np > 1)
+  {
+    const size_t bytes = 16 * sizeof(unsigned long long) + (size_t)4 * nx * sizeof(double);
+    if (b200vec_comm_peer_alloc(ctx, bytes, p->peers)) { delete p; return fail("peer allocation for the halo buffers"); }
+    p->have_peers = true;
+  }
+  p->time_rhs = getenv("B200_DIFFUSION_TIME_RHS") != nullptr;
+  if (p->time_rhs)
+  {
+    cudaEventCreate(&p->e0);
+    cudaEventCreate(&p->e1);
+  }
+  *out = p;
+  return 0;
+}
+
+int64_t b200_diffusion2d_plan_local_nodes(b200_diffusion2d_plan p) { return p ? p->nodes_loc : -1; }
+
+void b200_diffusion2d_plan_destroy(b200_diffusion2d_plan p)
+{
+  if (!p) return;
+  b200vec_ctx_sync(p->ctx);
+  if (p->have_peers) b200vec_comm_peer_free(p->ctx, p->peers);
+  if (p->d_tables) b200vec_free_device(p->ctx, p->d_tables, (size_t)(3 * p->nx + 2 * p->ny_loc) * sizeof(double));
+  if (p->e0) cudaEventDestroy(p->e0);
+  if (p->e1) cudaEventDestroy(p->e1);
+  delete p;
+}
+
+int b200_diffusion2d_rhs(b200_diffusion2d_plan p, double t, const double* u, double* f)
+{
+  RhsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u = u;
+  a.f = f;
+  a.nx = p->nx; a.ny = p->ny; a.ny_loc = p->ny_loc; a.js = p->js;
+  /* mpi_gpu/diffusion.cpp:77-79 */
+  a.cx = p->o.kx / (p->dx * p->dx);
+  a.cy = p->o.ky / (p->dy * p->dy);
+  a.cc = -2.0 * (a.cx + a.cy);
+  a.stct    = sin(PI_ * t) * cos(PI_ * t);
+  a.c2t     = cos(PI_ * t) * cos(PI_ * t);
+  a.forcing = p->o.forcing;
+  a.ax  = p->d_tables;
+  a.dcx = p->d_tables + p->nx;
+  a.ssx = p->d_tables + 2 * p->nx;
+  a.ssy = p->d_tables + 3 * p->nx;
+  a.dcy = p->d_tables + 3 * p->nx + p->ny_loc;
+  a.hasS = p->hasS;
+  a.hasN = p->hasN;
+  const unsigned long long seq = ++p->seq;
+  const int par                = (int)(seq & 1ull);
+  if (p->np > 1)
+  {
+    void* me = p->peers[p->rank];
+    if (p->hasS)
+    {
+      void* nb      = p->peers[p->rank - 1];
+      a.sendS       = nrecv_of(nb, p->nx, par); /* my first row is its "row from the north" */
+      a.ctrS_remote = ctr_of(nb, 1);
+      a.recvS       = srecv_of(me, p->nx, par);
+      a.ctrS_local  = ctr_of(me, 0);
+    }
+    if (p->hasN)
+    {
+      void* nb      = p->peers[p->rank + 1];
+      a.sendN       = srecv_of(nb, p->nx, par);
+      a.ctrN_remote = ctr_of(nb, 0);
+      a.recvN       = nrecv_of(me, p->nx, par);
+      a.ctrN_local  = ctr_of(me, 1);
+    }
+    a.expected = seq * (unsigned long long)p->tiles_x;
+  }
+  const int R = p->o.rows_per_cta;
+  dim3 grid((unsigned)p->tiles_x, (unsigned)((p->ny_loc + R - 1) / R));
+  cudaStream_t s = (cudaStream_t)b200vec_ctx_get_stream(p->ctx);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim            = grid;
+  cfg.blockDim           = dim3(kThreads);
+  cfg.stream             = s;
+  cudaLaunchAttribute at[1];
+  at[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs                                        = at;
+  cfg.numAttrs                                     = 1;
+  if (p->time_rhs) cudaEventRecord(p->e0, s);
+  cudaError_t e = (p->W == 4) ? cudaLaunchKernelEx(&cfg, k_diffusion_rhs<4>, a, R)
+                              : cudaLaunchKernelEx(&cfg, k_diffusion_rhs<1>, a, R);
+  if (e != cudaSuccess)
+  {
+    fprintf(stderr, "[diffusion2d_b200] RHS launch failed: %s\n", cudaGetErrorString(e));
+    return -1;
+  }
+  if (p->time_rhs)
+  {
+    cudaEventRecord(p->e1, s);
+    cudaEventSynchronize(p->e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p->e0, p->e1);
+    p->rhs_ms += ms;
+  }
+  p->rhs_calls++;
+  return 0;
+}
+
+int b200_diffusion2d_solution(b200_diffusion2d_plan p, double t, double* u)
+{
+  const double c2t = cos(PI_ * t) * cos(PI_ * t);
+  int64_t blocks   = (p->nodes_loc + kThreads - 1) / kThreads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  cudaStream_t s = (cudaStream_t)b200vec_ctx_get_stream(p->ctx);
+  k_solution<<<(unsigned)blocks, kThreads, 0, s>>>(u, p->nx, p->ny, p->ny_loc, p->js, p->d_tables + 2 * p->nx,
+                                                   p->d_tables + 3 * p->nx, c2t);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+} /* extern "C" */
+
+/* ---- callbacks handed to the (unmodified) integrator ------------------------ */
+namespace {
+
+int rhs_cb(sunrealtype t, N_Vector u, N_Vector f, void* user_data)
+{
+  auto* p = (b200_diffusion2d_plan)user_data;
+  return b200_diffusion2d_rhs(p, t, N_VGetDeviceArrayPointer_B200(u), N_VGetDeviceArrayPointer_B200(f));
+}
+
+/* preconditioner_jacobi.cpp:25-61 */
+int psetup_cb(sunrealtype, N_Vector, N_Vector, sunbooleantype, sunbooleantype*, sunrealtype gamma, void* user_data)
+{
+  auto* p         = (b200_diffusion2d_plan)user_data;
+  const double cx = p->o.kx / (p->dx * p->dx), cy = p->o.ky / (p->dy * p->dy);
+  const double cc = -2.0 * (cx + cy);
+  N_VConst(1.0 / (1.0 - gamma * cc), p->diag);
+  return 0;
+}
+int psolve_cb(sunrealtype, N_Vector, N_Vector, N_Vector r, N_Vector z, sunrealtype, sunrealtype, int, void* user_data)
+{
+  auto* p = (b200_diffusion2d_plan)user_data;
+  N_VProd(p->diag, r, z);
+  return 0;
+}
+
+/* UserOutput::write, diffusion_2D.cpp:778-846 */
+void write_row(b200_diffusion2d_plan p, double t, N_Vector u, N_Vector err, bool table, double* urms_out, double* max_out)
+{
+  double mx = 0.0;
+  if (err)
+  {
+    b200_diffusion2d_solution(p, t, N_VGetDeviceArrayPointer_B200(err));
+    N_VLinearSum(1.0, u, -1.0, err, err);
+    N_VAbs(err, err);
+    mx = N_VMaxNorm(err);
+  }
+  const double urms = sqrt(N_VDotProd(u, u) / (double)p->nx / (double)p->ny);
+  if (table && p->rank == 0)
+  {
+    if (err) printf("%22.15e%25.15e%25.15e\n", t, urms, mx);
+    else printf("%22.15e%25.15e\n", t, urms);
+  }
+  *urms_out = urms;
+  *max_out  = mx;
+}
+
+#define CHK(call, what)                                                        \
+  do {                                                                         \
+    int flag_ = (call);                                                        \
+    if (flag_ < 0)                                                             \
+    {                                                                          \
+      fprintf(stderr, "[diffusion2d_b200] %s failed with flag %d\n", what, flag_); \
+      return -1;                                                               \
+    }                                                                          \
+  } while (0)
+
+double now_s()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+extern "C" int b200_diffusion2d_run(b200vec_ctx ctx, const b200_diffusion2d_opts* opts, b200_diffusion2d_stats* st)
+{
+  if (!ctx || !opts || !st) return -1;
+  memset(st, 0, sizeof(*st));
+  const double t_setup0 = now_s();
+  b200_diffusion2d_plan p = nullptr;
+  if (b200_diffusion2d_plan_create(ctx, opts, &p)) return -1;
+  const bool table = opts->output > 0;
+
+  SUNContext sunctx = nullptr;
+  CHK(SUNContext_Create(SUN_COMM_NULL, &sunctx), "SUNContext_Create");
+
+  N_Vector u = N_VNewWithCtx_B200(p->nodes_loc, B200_MEM_DEVICE, ctx, sunctx);
+  if (!u) return fail("N_VNewWithCtx_B200");
+  if (p->np > 1 && N_VMakeDistributed_B200(u, p->nodes)) return fail("N_VMakeDistributed_B200");
+  if (opts->fused_ops) N_VEnableFusedOps_B200(u, SUNTRUE);
+
+  /* initial condition; error vector only with forcing (main_arkode.cpp:171-180) */
+  b200_diffusion2d_solution(p, 0.0, N_VGetDeviceArrayPointer_B200(u));
+  N_Vector err = opts->forcing ? N_VClone(u) : nullptr;
+
+  const int prectype = opts->preconditioning ? SUN_PREC_RIGHT : SUN_PREC_NONE; /* main_arkode.cpp:207 */
+  SUNLinearSolver LS = opts->ls_gmres ? SUNLinSol_SPGMR(u, prectype, opts->liniters, sunctx)
+                                      : SUNLinSol_PCG(u, prectype, opts->liniters, sunctx);
+  if (!LS) return fail("SUNLinSol constructor");
+  if (opts->preconditioning) p->diag = N_VClone(u);
+
+  void* mem = ARKStepCreate(nullptr, rhs_cb, 0.0, u, sunctx);
+  if (!mem) return fail("ARKStepCreate");
+  CHK(ARKodeSStolerances(mem, opts->rtol, opts->atol), "ARKodeSStolerances");
+  CHK(ARKodeSetUserData(mem, p), "ARKodeSetUserData");
+  CHK(ARKodeSetLinearSolver(mem, LS, nullptr), "ARKodeSetLinearSolver");
+  if (opts->preconditioning)
+  {
+    CHK(ARKodeSetPreconditioner(mem, psetup_cb, psolve_cb), "ARKodeSetPreconditioner");
+    CHK(ARKodeSetLSetupFrequency(mem, opts->msbp), "ARKodeSetLSetupFrequency");
+  }
+  CHK(ARKodeSetEpsLin(mem, opts->epslin), "ARKodeSetEpsLin");
+  CHK(ARKodeSetOrder(mem, opts->order), "ARKodeSetOrder");
+  if (opts->linear) CHK(ARKodeSetLinear(mem, 0), "ARKodeSetLinear");
+  CHK(ARKodeSetAdaptControllerByName(mem, opts->controller), "ARKodeSetAdaptControllerByName");
+  CHK(ARKodeSetMaxNumSteps(mem, opts->maxsteps), "ARKodeSetMaxNumSteps");
+  CHK(ARKodeSetStopTime(mem, opts->tf), "ARKodeSetStopTime");
+
+  if (table && p->rank == 0)
+  {
+    printf("\n");
+    if (err)
+    {
+      printf("          t                     ||u||_rms                max error      \n");
+      printf(" -----------------------------------------------------------------------\n");
+    }
+    else
+    {
+      printf("          t                     ||u||_rms      \n");
+      printf(" ----------------------------------------------\n");
+    }
+  }
+  double t = 0.0, urms = 0.0, mx = 0.0;
+  write_row(p, t, u, err, table, &urms, &mx);
+  b200vec_ctx_sync(ctx);
+  st->setup_seconds = now_s() - t_setup0;
+
+  const double dTout = opts->tf / opts->nout;
+  double tout        = dTout;
+  double evolve      = 0.0;
+  int rc             = 0;
+  for (int iout = 0; iout < opts->nout; iout++)
+  {
+    const double t0 = now_s();
+    const int flag  = ARKodeEvolve(mem, tout, u, &t, ARK_NORMAL);
+    b200vec_ctx_sync(ctx);
+    evolve += now_s() - t0;
+    if (flag < 0)
+    {
+      fprintf(stderr, "[diffusion2d_b200] ARKodeEvolve failed with flag %d\n", flag);
+      rc = -1;
+      break;
+    }
+    write_row(p, t, u, err, table, &urms, &mx);
+    tout += dTout;
+    tout = (tout > opts->tf) ? opts->tf : tout;
+  }
+  if (table && p->rank == 0)
+  {
+    printf(err ? " -----------------------------------------------------------------------\n\n"
+               : " ----------------------------------------------\n\n");
+    printf("Final integrator statistics:\n");
+    ARKodePrintAllStats(mem, stdout, SUN_OUTPUTFORMAT_TABLE);
+    fflush(stdout);
+  }
+  ARKodeGetNumSteps(mem, &st->nst);
+  ARKodeGetNumStepAttempts(mem, &st->nst_a);
+  ARKodeGetNumErrTestFails(mem, &st->netf);
+  ARKodeGetNumRhsEvals(mem, 0, &st->nfe);
+  ARKodeGetNumRhsEvals(mem, 1, &st->nfi);
+  ARKodeGetNumNonlinSolvIters(mem, &st->nni);
+  ARKodeGetNumNonlinSolvConvFails(mem, &st->ncfn);
+  ARKodeGetNumLinSolvSetups(mem, &st->nsetups);
+  ARKodeGetNumLinIters(mem, &st->nli);
+  ARKodeGetNumLinConvFails(mem, &st->nlcf);
+  if (opts->preconditioning)
+  {
+    ARKodeGetNumPrecEvals(mem, &st->npe);
+    ARKodeGetNumPrecSolves(mem, &st->nps);
+  }
+  ARKodeGetNumJtimesEvals(mem, &st->njv);
+  ARKodeGetNumLinRhsEvals(mem, &st->nfeLS);
+  st->t_final        = t;
+  st->urms           = urms;
+  st->max_err        = mx;
+  st->evolve_seconds = evolve;
+  st->rhs_seconds    = p->rhs_ms * 1e-3;
+  st->rhs_calls      = p->rhs_calls;
+  st->nodes          = p->nodes;
+  st->nodes_loc      = p->nodes_loc;
+  st->nranks         = p->np;
+
+  ARKodeFree(&mem);
+  SUNLinSolFree(LS);
+  if (p->diag) N_VDestroy(p->diag);
+  if (err) N_VDestroy(err);
+  N_VDestroy(u);
+  b200_diffusion2d_plan_destroy(p);
+  SUNContext_Free(&sunctx);
+  return rc;
+}
