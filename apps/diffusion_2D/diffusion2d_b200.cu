@@ -51,7 +51,7 @@ struct RhsArgs
   double cx, cy, cc;
   double stct, c2t; /* sin(pi t) cos(pi t), cos^2(pi t) */
   int forcing;
-  const double *ax, *dcx, *ssx; /* per x: (-2 pi) sin^2, bx (cos^2 - sin^2), sin^2 */
+  const double *dcx, *ssx;      /* per x: bx (cos^2 - sin^2), sin^2                    */
   const double *ssy, *dcy;      /* per local y: sin^2, by (cos^2 - sin^2)          */
   /* halo exchange over peer memory */
   int hasS, hasN;
@@ -111,45 +111,59 @@ __device__ __forceinline__ void wait_counter(const unsigned long long* ctr, unsi
   __syncthreads();
 }
 
-/* one stencil row: s/c/n = south/centre/north values of this thread's W points */
+/* one row of this thread's W points in flight: the values and, in lane 0 / lane 31
+   only, the west / east neighbour of the thread's span (the other lanes get theirs by
+   shuffle).  Loaded together so that no stencil row waits on a dependent load. */
+template <int W>
+struct Row
+{
+  double v[W];
+  double edge;
+};
+
+template <int W>
+__device__ __forceinline__ void load_row(const RhsArgs& a, int64_t j, int64_t xo, int64_t x0, int lane, Row<W>& r)
+{
+  const double* row = a.u + j * a.nx;
+  ld_row<W>(row + xo, r.v);
+  if (lane == 0 && x0 > 0 && x0 < a.nx) r.edge = row[x0 - 1];
+  if (lane == 31 && x0 + W < a.nx) r.edge = row[x0 + W];
+}
+
+/* one stencil row: s/c/n = south/centre/north values of this thread's W points;
+   sy, dy = the row's forcing factors sin^2(pi y), by (cos^2 - sin^2)(pi y) */
 template <int W>
 __device__ __forceinline__ void compute_row(const RhsArgs& a, int64_t j, int64_t x0, bool act, const double (&s)[W],
-                                            const double (&c)[W], const double (&n)[W], const double (&tax)[W],
+                                            const Row<W>& c, const double (&n)[W], double sy, double dy,
                                             const double (&tdcx)[W], const double (&tssx)[W])
 {
-  /* west / east neighbours: lanes exchange their edge values, warp edges read memory */
+  /* west / east neighbours: lanes exchange their edge values, warp edges were prefetched */
   const int lane = threadIdx.x & 31;
-  double w = __shfl_up_sync(0xffffffffu, c[W - 1], 1);
-  double e = __shfl_down_sync(0xffffffffu, c[0], 1);
+  double w = __shfl_up_sync(0xffffffffu, c.v[W - 1], 1);
+  double e = __shfl_down_sync(0xffffffffu, c.v[0], 1);
   if (!act) return;
-  const double* row = a.u + j * a.nx;
-  if (lane == 0 && x0 > 0) w = row[x0 - 1];
-  if (lane == 31 && x0 + W < a.nx) e = row[x0 + W];
-  const int64_t jg   = a.js + j;
-  const bool ybound  = (jg == 0) || (jg == a.ny - 1);
-  double sy = 0.0, dy = 0.0;
-  if (a.forcing && !ybound)
-  {
-    sy = a.ssy[j];
-    dy = a.dcy[j];
-  }
+  if (lane == 0) w = c.edge;
+  if (lane == 31) e = c.edge;
+  const int64_t jg  = a.js + j;
+  const bool ybound = (jg == 0) || (jg == a.ny - 1);
   double r[W];
 #pragma unroll
   for (int k = 0; k < W; k++)
   {
     const int64_t i = x0 + k;
-    const double uw = (k == 0) ? w : c[k - 1];
-    const double ue = (k == W - 1) ? e : c[k + 1];
+    const double uw = (k == 0) ? w : c.v[k - 1];
+    const double ue = (k == W - 1) ? e : c.v[k + 1];
     double v        = 0.0;
     if (!ybound && i > 0 && i < a.nx - 1)
     {
       /* mpi_serial/diffusion.cpp:98-101 / mpi_gpu/diffusion.cpp:83 */
-      v = a.cc * c[k] + a.cx * (uw + ue) + a.cy * (s[k] + n[k]);
+      v = a.cc * c.v[k] + a.cx * (uw + ue) + a.cy * (s[k] + n[k]);
       if (a.forcing)
       {
         /* -2 pi sin^2x sin^2y sin t cos t - bx (cos^2x - sin^2x) sin^2y cos^2t
-           - by (cos^2y - sin^2y) sin^2x cos^2t, left to right as the reference writes it */
-        const double b = tax[k] * sy * a.stct - tdcx[k] * sy * a.c2t - dy * tssx[k] * a.c2t;
+           - by (cos^2y - sin^2y) sin^2x cos^2t, left to right as the reference writes it
+           (mpi_serial/diffusion.cpp:82-85) */
+        const double b = (-2.0 * PI_) * tssx[k] * sy * a.stct - tdcx[k] * sy * a.c2t - dy * tssx[k] * a.c2t;
         v += b;
       }
     }
@@ -158,11 +172,18 @@ __device__ __forceinline__ void compute_row(const RhsArgs& a, int64_t j, int64_t
   st_row<W>(a.f + j * a.nx + x0, r);
 }
 
-template <int W>
-__global__ void __launch_bounds__(kThreads) k_diffusion_rhs(const __grid_constant__ RhsArgs a, int R)
+constexpr int kMaxRows = 512; /* rows per CTA whose y factors are staged in shared memory */
+
+/* LA = rows of look-ahead: the ring keeps rows j-1 .. j+LA of the thread's span in
+   registers, i.e. LA x 32 B per thread are in flight while row j is computed. */
+template <int W, int LA, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_diffusion_rhs(const __grid_constant__ RhsArgs a, int R)
 {
+  constexpr int NR = LA + 2;
+  __shared__ double s_sy[kMaxRows], s_dy[kMaxRows];
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int lane   = threadIdx.x & 31;
   const int64_t x0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * W;
   const bool act   = x0 < a.nx;
   /* row blocks: the two that own the strip's first and last rows are scheduled
@@ -199,37 +220,61 @@ __global__ void __launch_bounds__(kThreads) k_diffusion_rhs(const __grid_constan
     }
   }
 
-  double tax[W], tdcx[W], tssx[W];
+  double tdcx[W], tssx[W];
 #pragma unroll
-  for (int k = 0; k < W; k++) tax[k] = tdcx[k] = tssx[k] = 0.0;
-  if (a.forcing && act)
+  for (int k = 0; k < W; k++) tdcx[k] = tssx[k] = 0.0;
+  if (a.forcing)
   {
-    ld_row<W>(a.ax + xo, tax);
-    ld_row<W>(a.dcx + xo, tdcx);
-    ld_row<W>(a.ssx + xo, tssx);
+    if (act)
+    {
+      ld_row<W>(a.dcx + xo, tdcx);
+      ld_row<W>(a.ssx + xo, tssx);
+    }
+    for (int64_t j = jb + threadIdx.x; j < je; j += kThreads)
+    {
+      s_sy[j - jb] = a.ssy[j];
+      s_dy[j - jb] = a.dcy[j];
+    }
   }
+  else
+    for (int j = threadIdx.x; j < kMaxRows; j += kThreads) s_sy[j] = s_dy[j] = 0.0;
+  __syncthreads();
 
-  /* ---- 2. march the rows that need no halo: [m0, m1), two rows of look-ahead */
+  /* ---- 2. march the rows that need no halo: [m0, m1) */
   const int64_t m0 = jb + (ownS ? 1 : 0);
   const int64_t m1 = je - (ownN ? 1 : 0);
   if (m0 < m1)
   {
-    double prev[W], cur[W], nxt[W], nxt2[W];
+    /* highest row any stencil of [m0, m1) touches (a global-boundary row needs no
+       neighbours: its result is 0) */
+    const int64_t top = (m1 < a.ny_loc) ? m1 : a.ny_loc - 1;
+    Row<W> ring[NR];
 #pragma unroll
-    for (int k = 0; k < W; k++) prev[k] = cur[k] = nxt[k] = nxt2[k] = 0.0;
-    if (m0 > 0) ld_row<W>(a.u + (m0 - 1) * a.nx + xo, prev);
-    ld_row<W>(a.u + m0 * a.nx + xo, cur);
-    if (m0 + 1 < a.ny_loc) ld_row<W>(a.u + (m0 + 1) * a.nx + xo, nxt);
-    for (int64_t j = m0; j < m1; j++)
+    for (int s = 0; s < NR; s++)
     {
-      if (j + 1 < m1 && j + 2 < a.ny_loc) ld_row<W>(a.u + (j + 2) * a.nx + xo, nxt2);
-      compute_row<W>(a, j, x0, act, prev, cur, nxt, tax, tdcx, tssx);
 #pragma unroll
-      for (int k = 0; k < W; k++)
+      for (int k = 0; k < W; k++) ring[s].v[k] = 0.0;
+      ring[s].edge = 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < NR; s++)
+    {
+      const int64_t row = m0 - 1 + s;
+      if (row >= 0 && row <= top) load_row<W>(a, row, xo, x0, lane, ring[s]);
+    }
+    for (int64_t jj = m0; jj < m1; jj += NR)
+    {
+#pragma unroll
+      for (int k = 0; k < NR; k++)
       {
-        prev[k] = cur[k];
-        cur[k]  = nxt[k];
-        nxt[k]  = nxt2[k];
+        const int64_t j = jj + k;
+        if (j < m1)
+        {
+          compute_row<W>(a, j, x0, act, ring[k].v, ring[(k + 1) % NR], ring[(k + 2) % NR].v, s_sy[j - jb],
+                         s_dy[j - jb], tdcx, tssx);
+          const int64_t nr = j + NR - 1; /* the row that replaces row j-1 in the ring */
+          if (nr <= top) load_row<W>(a, nr, xo, x0, lane, ring[k]);
+        }
       }
     }
   }
@@ -238,21 +283,23 @@ __global__ void __launch_bounds__(kThreads) k_diffusion_rhs(const __grid_constan
   if (ownN)
   {
     const int64_t j = a.ny_loc - 1;
-    double s[W], c[W], n[W];
-    ld_row<W>(a.u + (j - 1) * a.nx + xo, s);
-    ld_row<W>(a.u + j * a.nx + xo, c);
+    Row<W> s, c, n;
+    s.edge = c.edge = n.edge = 0.0;
+    load_row<W>(a, j - 1, xo, x0, lane, s);
+    load_row<W>(a, j, xo, x0, lane, c);
     wait_counter(a.ctrN_local, a.expected);
-    ld_halo<W>(a.recvN + xo, n);
-    compute_row<W>(a, j, x0, act, s, c, n, tax, tdcx, tssx);
+    ld_halo<W>(a.recvN + xo, n.v);
+    compute_row<W>(a, j, x0, act, s.v, c, n.v, s_sy[j - jb], s_dy[j - jb], tdcx, tssx);
   }
   if (ownS)
   {
-    double s[W], c[W], n[W];
-    ld_row<W>(a.u + xo, c);
-    ld_row<W>(a.u + a.nx + xo, n);
+    Row<W> s, c, n;
+    s.edge = c.edge = n.edge = 0.0;
+    load_row<W>(a, 0, xo, x0, lane, c);
+    load_row<W>(a, 1, xo, x0, lane, n);
     wait_counter(a.ctrS_local, a.expected);
-    ld_halo<W>(a.recvS + xo, s);
-    compute_row<W>(a, 0, x0, act, s, c, n, tax, tdcx, tssx);
+    ld_halo<W>(a.recvS + xo, s.v);
+    compute_row<W>(a, 0, x0, act, s.v, c, n.v, s_sy[0], s_dy[0], tdcx, tssx);
   }
 }
 
@@ -274,15 +321,33 @@ __global__ void __launch_bounds__(kThreads) k_solution(double* u, int64_t nx, in
 
 } // namespace
 
+namespace {
+/* look-ahead / residency variants of the RHS kernel (B200_DIFFUSION_VARIANT picks one; tuning) */
+typedef void (*rhs_kernel_t)(const RhsArgs, int);
+struct RhsVariant
+{
+  const char* name;
+  rhs_kernel_t k4, k1;
+};
+const RhsVariant kVariants[] = {
+  {"la4x2", k_diffusion_rhs<4, 4, 2>, k_diffusion_rhs<1, 4, 2>}, /* default */
+  {"la2x4", k_diffusion_rhs<4, 2, 4>, k_diffusion_rhs<1, 2, 4>},
+  {"la3x3", k_diffusion_rhs<4, 3, 3>, k_diffusion_rhs<1, 3, 3>},
+  {"la6x2", k_diffusion_rhs<4, 6, 2>, k_diffusion_rhs<1, 6, 2>},
+  {"la8x1", k_diffusion_rhs<4, 8, 1>, k_diffusion_rhs<1, 8, 1>},
+};
+} // namespace
+
 struct b200_diffusion2d_plan_s
 {
+  rhs_kernel_t kernel = nullptr;
   b200vec_ctx ctx     = nullptr;
   b200_diffusion2d_opts o;
   int rank = 0, np = 1;
   int64_t nx = 0, ny = 0, ny_loc = 0, js = 0, nodes = 0, nodes_loc = 0;
   double dx = 0, dy = 0;
   int hasS = 0, hasN = 0;
-  double* d_tables = nullptr; /* ax | dcx | ssx (nx each) | ssy | dcy (ny_loc each) */
+  double* d_tables = nullptr; /* dcx | ssx (nx each) | ssy | dcy (ny_loc each) */
   /* symmetric halo region: [16 u64 counters][Srecv 2 x nx][Nrecv 2 x nx] */
   void* peers[8]          = {nullptr};
   bool have_peers         = false;
@@ -335,7 +400,7 @@ void b200_diffusion2d_default_opts(b200_diffusion2d_opts* o)
   o->output       = 1;
   o->nout         = 20;
   o->fused_ops    = 1;
-  o->rows_per_cta = 32;
+  o->rows_per_cta = 0;
 }
 
 int b200_diffusion2d_plan_create(b200vec_ctx ctx, const b200_diffusion2d_opts* opts, b200_diffusion2d_plan* out)
@@ -365,27 +430,50 @@ int b200_diffusion2d_plan_create(b200vec_ctx ctx, const b200_diffusion2d_opts* o
   }
   p->W       = (p->nx % 4 == 0) ? 4 : 1;
   p->tiles_x = (int)((p->nx + (int64_t)kThreads * p->W - 1) / ((int64_t)kThreads * p->W));
-  if (p->o.rows_per_cta < 2) p->o.rows_per_cta = 2;
+  /* rows per CTA: by default ONE wave of equal row blocks -- (resident CTAs per SM x SMs)
+     CTAs, every CTA marching the same number of rows, so there is no tail wave and only
+     2 halo rows are re-read per R rows; rows_per_cta > 0 overrides (tuning) */
+  {
+    int dev = 0, sms = 148, occ = 2;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const RhsVariant* var = &kVariants[0];
+    if (const char* want = getenv("B200_DIFFUSION_VARIANT"))
+      for (const RhsVariant& v : kVariants)
+        if (!strcmp(v.name, want)) var = &v;
+    p->kernel = (p->W == 4) ? var->k4 : var->k1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->kernel, kThreads, 0);
+    if (occ < 1) occ = 1;
+    int64_t R = p->o.rows_per_cta;
+    if (R <= 0)
+    {
+      int64_t blocks_y = ((int64_t)sms * occ) / p->tiles_x;
+      if (blocks_y < 1) blocks_y = 1;
+      R = (p->ny_loc + blocks_y - 1) / blocks_y;
+    }
+    if (R < 2) R = 2;
+    if (R > kMaxRows) R = kMaxRows;
+    p->o.rows_per_cta = (int)R;
+  }
 
   /* factor tables with the HOST libm: the same factors the reference's CPU
      code evaluates per point (mpi_serial/diffusion.cpp:60-90) */
   const int64_t nx = p->nx, nyl = p->ny_loc;
-  std::vector<double> t(3 * nx + 2 * nyl);
+  std::vector<double> t(2 * nx + 2 * nyl);
   const double bx = opts->kx * 2.0 * PI_ * PI_, by = opts->ky * 2.0 * PI_ * PI_;
   for (int64_t i = 0; i < nx; i++)
   {
     const double x   = (double)i * p->dx;
     const double ssx = sin(PI_ * x) * sin(PI_ * x), csx = cos(PI_ * x) * cos(PI_ * x);
-    t[i]             = -2.0 * PI_ * ssx;
-    t[nx + i]        = bx * (csx - ssx);
-    t[2 * nx + i]    = ssx;
+    t[i]             = bx * (csx - ssx);
+    t[nx + i]        = ssx;
   }
   for (int64_t j = 0; j < nyl; j++)
   {
     const double y   = (double)(p->js + j) * p->dy;
     const double ssy = sin(PI_ * y) * sin(PI_ * y), csy = cos(PI_ * y) * cos(PI_ * y);
-    t[3 * nx + j]       = ssy;
-    t[3 * nx + nyl + j] = by * (csy - ssy);
+    t[2 * nx + j]       = ssy;
+    t[2 * nx + nyl + j] = by * (csy - ssy);
   }
   void* d = nullptr;
   if (b200vec_malloc_device(ctx, t.size() * sizeof(double), &d)) { delete p; return fail("table allocation"); }
@@ -415,7 +503,7 @@ void b200_diffusion2d_plan_destroy(b200_diffusion2d_plan p)
   if (!p) return;
   b200vec_ctx_sync(p->ctx);
   if (p->have_peers) b200vec_comm_peer_free(p->ctx, p->peers);
-  if (p->d_tables) b200vec_free_device(p->ctx, p->d_tables, (size_t)(3 * p->nx + 2 * p->ny_loc) * sizeof(double));
+  if (p->d_tables) b200vec_free_device(p->ctx, p->d_tables, (size_t)(2 * p->nx + 2 * p->ny_loc) * sizeof(double));
   if (p->e0) cudaEventDestroy(p->e0);
   if (p->e1) cudaEventDestroy(p->e1);
   delete p;
@@ -435,11 +523,10 @@ int b200_diffusion2d_rhs(b200_diffusion2d_plan p, double t, const double* u, dou
   a.stct    = sin(PI_ * t) * cos(PI_ * t);
   a.c2t     = cos(PI_ * t) * cos(PI_ * t);
   a.forcing = p->o.forcing;
-  a.ax  = p->d_tables;
-  a.dcx = p->d_tables + p->nx;
-  a.ssx = p->d_tables + 2 * p->nx;
-  a.ssy = p->d_tables + 3 * p->nx;
-  a.dcy = p->d_tables + 3 * p->nx + p->ny_loc;
+  a.dcx = p->d_tables;
+  a.ssx = p->d_tables + p->nx;
+  a.ssy = p->d_tables + 2 * p->nx;
+  a.dcy = p->d_tables + 2 * p->nx + p->ny_loc;
   a.hasS = p->hasS;
   a.hasN = p->hasN;
   const unsigned long long seq = ++p->seq;
@@ -478,8 +565,7 @@ int b200_diffusion2d_rhs(b200_diffusion2d_plan p, double t, const double* u, dou
   cfg.attrs                                        = at;
   cfg.numAttrs                                     = 1;
   if (p->time_rhs) cudaEventRecord(p->e0, s);
-  cudaError_t e = (p->W == 4) ? cudaLaunchKernelEx(&cfg, k_diffusion_rhs<4>, a, R)
-                              : cudaLaunchKernelEx(&cfg, k_diffusion_rhs<1>, a, R);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, p->kernel, a, R);
   if (e != cudaSuccess)
   {
     fprintf(stderr, "[diffusion2d_b200] RHS launch failed: %s\n", cudaGetErrorString(e));
@@ -504,8 +590,8 @@ int b200_diffusion2d_solution(b200_diffusion2d_plan p, double t, double* u)
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   cudaStream_t s = (cudaStream_t)b200vec_ctx_get_stream(p->ctx);
-  k_solution<<<(unsigned)blocks, kThreads, 0, s>>>(u, p->nx, p->ny, p->ny_loc, p->js, p->d_tables + 2 * p->nx,
-                                                   p->d_tables + 3 * p->nx, c2t);
+  k_solution<<<(unsigned)blocks, kThreads, 0, s>>>(u, p->nx, p->ny, p->ny_loc, p->js, p->d_tables + p->nx,
+                                                   p->d_tables + 2 * p->nx, c2t);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

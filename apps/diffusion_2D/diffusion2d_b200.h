@@ -48,7 +48,7 @@ typedef struct
   int nout;   /* number of output times (20)                             */
   /* vector options */
   int fused_ops; /* N_VEnableFusedOps_B200 (1)                           */
-  int rows_per_cta; /* RHS kernel: rows marched per CTA (32)             */
+  int rows_per_cta; /* RHS kernel: rows marched per CTA; 0 = one wave of equal row blocks (0) */
 } b200_diffusion2d_opts;
 
 typedef struct

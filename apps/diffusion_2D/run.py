@@ -118,7 +118,7 @@ def main():
     ap.add_argument("--output", type=int, default=1)
     ap.add_argument("--nout", type=int, default=20)
     ap.add_argument("--nofused", action="store_true", help="leave the fused N_Vector ops disabled")
-    ap.add_argument("--rows-per-cta", type=int, default=32)
+    ap.add_argument("--rows-per-cta", type=int, default=0, help="0 = one wave of equal row blocks")
     ap.add_argument("--exact-threshold", type=int, default=None,
                     help="vector length up to which reductions sum in serial order (<= 4096)")
     ap.add_argument("--json", action="store_true")

@@ -289,6 +289,46 @@ def _init_values(vec, host_view, rng, n):
     host_view(vec["CN"])[...] = rng.integers(-2, 3, n).astype(np.float64)
 
 
+def run_diffusion(ctx, world, args):
+    """Bounded solve of the re-hosted ARKODE diffusion_2D benchmark (apps/diffusion_2D) on the
+    bench's own context: nx x (ny * world) mesh, strips in y, dx = dy fixed (yu = world), so
+    the per-GPU work is the BASELINE config (8192^2 per GPU, DIRK-3 + PCG(20) + Jacobi)."""
+    sys.path.insert(0, str(ROOT / "apps" / "diffusion_2D"))
+    import run as app
+
+    n = args.diffusion_n
+    st = app.run(ctx, nx=n, ny=n * world, yu=float(world), tf=args.diffusion_tf, nout=1, output=0)
+    ev = st["evolve_seconds"]
+    return {
+        "workload": f"benchmarks/diffusion_2D re-host: {n} x {n * world} mesh ({n}^2 per GPU, strips in y, "
+                    f"dx = dy = 1/{n - 1}), ARKODE DIRK order 3, PCG liniters 20, Jacobi, rtol 1e-5 atol 1e-10, "
+                    f"tf = {args.diffusion_tf} (bounded: the full tf = 1 run is ~1e4 x longer)",
+        "solve_s": round(ev, 4), "steps": st["nst"], "step_attempts": st["nst_a"], "ls_iters": st["nli"],
+        "rhs_evals": st["rhs_calls"], "ms_per_ls_iter": round(ev / max(st["nli"], 1) * 1e3, 4),
+        "ns_per_node_per_ls_iter": round(ev / max(st["nli"], 1) / st["nodes"] * world * 1e9, 5),
+        "nodes_per_gpu": st["nodes_loc"], "max_err": st["max_err"],
+    }
+
+
+def run_diffusion_cpu_reference(n=2048, tf=1e-5):
+    """The reference's own benchmarks/diffusion_2D (CPU backend, one rank: no MPI in this
+    image) on a bounded sample: oracle/_ref/bin/arkode_diffusion_2D_ref."""
+    import re
+
+    exe = ROOT / "oracle" / "_ref" / "bin" / "arkode_diffusion_2D_ref"
+    if not exe.exists():
+        return {"unavailable": f"{exe} missing"}
+    t0 = time.perf_counter()
+    r = subprocess.run([str(exe), "--nx", str(n), "--ny", str(n), "--tf", str(tf), "--nout", "1"],
+                       capture_output=True, text=True, timeout=600)
+    dt = time.perf_counter() - t0
+    m = re.search(r"^LS iters\s*=\s*(\d+)", r.stdout, re.M)
+    nli = int(m.group(1)) if m else 0
+    return {"kind": "reference", "cores": 1, "sample": f"{n}^2 mesh, tf = {tf}, whole program wall time",
+            "wall_s": round(dt, 3), "ls_iters": nli,
+            "ns_per_node_per_ls_iter": round(dt / max(nli, 1) / (n * n) * 1e9, 3)}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -543,11 +583,25 @@ def b200_arm(args):
         except Exception:
             pass
 
+    # ---- ARKODE diffusion_2D solve time (second half of BASELINE's metric); collective
+    diffusion = None
+    if not args.no_diffusion:
+        try:
+            diffusion = run_diffusion(ctx, world, args)
+        except Exception as e:  # reported, never required for the op-suite line
+            diffusion = {"unavailable": f"{type(e).__name__}: {e}"}
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
         return 0
+
+    if diffusion is not None and "solve_s" in diffusion and world == 1 and not args.no_cpu_baseline:
+        try:
+            diffusion["cpu_reference"] = run_diffusion_cpu_reference()
+        except Exception as e:
+            diffusion["cpu_reference"] = {"unavailable": str(e)}
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
@@ -576,6 +630,7 @@ def b200_arm(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
+        "diffusion_2D": diffusion,
         "per_op": per_op,
         "result_checksum": result_value,
         "ops_per_step": len(suite),
@@ -597,6 +652,9 @@ def main():
     ap.add_argument("--log2n", type=int, default=24, help="log2 of the vector length per GPU")
     ap.add_argument("--cpu-log2n", type=int, default=22, help="length of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-diffusion", action="store_true", help="skip the ARKODE diffusion_2D leg")
+    ap.add_argument("--diffusion-n", type=int, default=8192, help="mesh points per GPU in x and y")
+    ap.add_argument("--diffusion-tf", type=float, default=1e-4)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
