@@ -130,20 +130,14 @@ __device__ __forceinline__ void load_row(const RhsArgs& a, int64_t j, int64_t xo
   if (lane == 31 && x0 + W < a.nx) r.edge = row[x0 + W];
 }
 
-/* one stencil row: s/c/n = south/centre/north values of this thread's W points;
-   sy, dy = the row's forcing factors sin^2(pi y), by (cos^2 - sin^2)(pi y) */
+/* one stencil row: s/c/n = south/centre/north values of this thread's W points, w/e the
+   west/east neighbours of the span; sy, dy = the row's forcing factors sin^2(pi y),
+   by (cos^2 - sin^2)(pi y).  Arithmetic in the reference's order (-fmad=false). */
 template <int W>
-__device__ __forceinline__ void compute_row(const RhsArgs& a, int64_t j, int64_t x0, bool act, const double (&s)[W],
-                                            const Row<W>& c, const double (&n)[W], double sy, double dy,
-                                            const double (&tdcx)[W], const double (&tssx)[W])
+__device__ __forceinline__ void stencil_store(const RhsArgs& a, int64_t j, int64_t x0, const double (&s)[W],
+                                              const double (&c)[W], const double (&n)[W], double w, double e, double sy,
+                                              double dy, const double (&tdcx)[W], const double (&tssx)[W])
 {
-  /* west / east neighbours: lanes exchange their edge values, warp edges were prefetched */
-  const int lane = threadIdx.x & 31;
-  double w = __shfl_up_sync(0xffffffffu, c.v[W - 1], 1);
-  double e = __shfl_down_sync(0xffffffffu, c.v[0], 1);
-  if (!act) return;
-  if (lane == 0) w = c.edge;
-  if (lane == 31) e = c.edge;
   const int64_t jg  = a.js + j;
   const bool ybound = (jg == 0) || (jg == a.ny - 1);
   double r[W];
@@ -151,13 +145,13 @@ __device__ __forceinline__ void compute_row(const RhsArgs& a, int64_t j, int64_t
   for (int k = 0; k < W; k++)
   {
     const int64_t i = x0 + k;
-    const double uw = (k == 0) ? w : c.v[k - 1];
-    const double ue = (k == W - 1) ? e : c.v[k + 1];
+    const double uw = (k == 0) ? w : c[k - 1];
+    const double ue = (k == W - 1) ? e : c[k + 1];
     double v        = 0.0;
     if (!ybound && i > 0 && i < a.nx - 1)
     {
       /* mpi_serial/diffusion.cpp:98-101 / mpi_gpu/diffusion.cpp:83 */
-      v = a.cc * c.v[k] + a.cx * (uw + ue) + a.cy * (s[k] + n[k]);
+      v = a.cc * c[k] + a.cx * (uw + ue) + a.cy * (s[k] + n[k]);
       if (a.forcing)
       {
         /* -2 pi sin^2x sin^2y sin t cos t - bx (cos^2x - sin^2x) sin^2y cos^2t
@@ -170,6 +164,21 @@ __device__ __forceinline__ void compute_row(const RhsArgs& a, int64_t j, int64_t
     r[k] = v;
   }
   st_row<W>(a.f + j * a.nx + x0, r);
+}
+
+/* register path: west / east neighbours by warp shuffle, warp edges prefetched */
+template <int W>
+__device__ __forceinline__ void compute_row(const RhsArgs& a, int64_t j, int64_t x0, bool act, const double (&s)[W],
+                                            const Row<W>& c, const double (&n)[W], double sy, double dy,
+                                            const double (&tdcx)[W], const double (&tssx)[W])
+{
+  const int lane = threadIdx.x & 31;
+  double w = __shfl_up_sync(0xffffffffu, c.v[W - 1], 1);
+  double e = __shfl_down_sync(0xffffffffu, c.v[0], 1);
+  if (!act) return;
+  if (lane == 0) w = c.edge;
+  if (lane == 31) e = c.edge;
+  stencil_store<W>(a, j, x0, s, c.v, n, w, e, sy, dy, tdcx, tssx);
 }
 
 constexpr int kMaxRows = 512; /* rows per CTA whose y factors are staged in shared memory */
@@ -303,6 +312,250 @@ __global__ void __launch_bounds__(kThreads, MINB) k_diffusion_rhs(const __grid_c
   }
 }
 
+/* ------------------------------------------------------------------------------------
+ * TMA path (nx % 4 == 0, 16-byte aligned u): the rows of the CTA's x-tile stream through a
+ * ring of kStages shared-memory stages filled by 1-D bulk copies (cp.async.bulk, one
+ * elected producer thread, mbarrier complete_tx), so the bytes in flight per SM are set by
+ * shared memory (2 CTAs x 11 rows x 8 KB = 180 KB) and not by registers -- the register
+ * march above tops out at ~64 KB in flight per SM and 4.2 TB/s (profiles/r01_rhs_*).
+ * 8 consumer warps keep the south and centre rows in registers, read the new north row and
+ * the two x-neighbours of their span from the ring, and release a stage (empty mbarrier)
+ * once it has served as centre row.  The halo-dependent first / last row of the strip is
+ * finished afterwards by the register path, exactly as in k_diffusion_rhs.
+ * ------------------------------------------------------------------------------------ */
+constexpr int kTX        = kThreads * 4; /* x-points per CTA tile */
+constexpr int kStages    = 12;
+constexpr int kRowDbl    = kTX + 4; /* a stage holds x0-2 .. x0+kTX+1 (16-byte aligned both ends) */
+constexpr int kTmaRows   = 256;     /* max rows per CTA (y factors staged in shared memory) */
+constexpr int kTmaThreads = kThreads + 32;
+constexpr size_t kTmaSmem = 256 + (size_t)kStages * kRowDbl * sizeof(double);
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+  uint32_t ok          = 0, spins = 0;
+  unsigned long long t0 = 0;
+  for (;;)
+  {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (ok) return;
+    if ((++spins & 0x3ffu) == 0)
+    {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) asm volatile("trap;"); /* a lost copy must not hang the GPU */
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void lds4(const double* p, double (&v)[4])
+{
+  const uint32_t a = smem_addr(p);
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a) : "memory");
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "r"(a + 16) : "memory");
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 2) k_diffusion_rhs_tma(const __grid_constant__ RhsArgs a, int R)
+{
+  constexpr int W = 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_sy[kTmaRows], s_dy[kTmaRows];
+  const uint32_t bar_full  = smem_addr(smem_raw);                 /* kStages x 8 B */
+  const uint32_t bar_empty = bar_full + 8 * kStages;              /* kStages x 8 B */
+  double* const ring       = (double*)(smem_raw + 256);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int tid       = threadIdx.x;
+  const int lane      = tid & 31;
+  const bool consumer = tid < kThreads;
+  const int64_t xt    = (int64_t)blockIdx.x * kTX; /* first x of the tile */
+  const int64_t x0    = consumer ? xt + (int64_t)tid * W : a.nx;
+  const bool act      = x0 < a.nx;
+  const int nyb       = gridDim.y;
+  int yb              = blockIdx.y;
+  if (nyb > 2) yb = (blockIdx.y == 0) ? 0 : (blockIdx.y == 1) ? nyb - 1 : blockIdx.y - 1;
+  const int64_t jb = (int64_t)yb * R;
+  const int64_t je = (jb + R < a.ny_loc) ? jb + R : a.ny_loc;
+  const bool ownS  = (jb == 0) && a.hasS;
+  const bool ownN  = (je == a.ny_loc) && a.hasN;
+  const int64_t xo = act ? x0 : 0;
+
+  if (tid == 0)
+  {
+    for (int s = 0; s < kStages; s++)
+    {
+      mbar_init(bar_full + 8 * s, 1);               /* the producer's expect_tx arrive */
+      mbar_init(bar_empty + 8 * s, kThreads / 32);  /* one arrive per consumer warp    */
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+
+  /* ---- 1. push the boundary rows to the neighbours */
+  if (ownS || ownN)
+  {
+    double v[W];
+    if (ownS && act)
+    {
+      ld_row<W>(a.u + xo, v);
+      st_row<W>(a.sendS + xo, v);
+    }
+    if (ownN && act)
+    {
+      ld_row<W>(a.u + (a.ny_loc - 1) * a.nx + xo, v);
+      st_row<W>(a.sendN + xo, v);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0)
+    {
+      if (ownS) atomicAdd_system(a.ctrS_remote, 1ull);
+      if (ownN) atomicAdd_system(a.ctrN_remote, 1ull);
+    }
+  }
+
+  double tdcx[W], tssx[W];
+#pragma unroll
+  for (int k = 0; k < W; k++) tdcx[k] = tssx[k] = 0.0;
+  if (a.forcing)
+  {
+    if (act)
+    {
+      ld_row<W>(a.dcx + xo, tdcx);
+      ld_row<W>(a.ssx + xo, tssx);
+    }
+    for (int64_t j = jb + tid; j < je; j += kTmaThreads)
+    {
+      s_sy[j - jb] = a.ssy[j];
+      s_dy[j - jb] = a.dcy[j];
+    }
+  }
+  else
+    for (int j = tid; j < kTmaRows; j += kTmaThreads) s_sy[j] = s_dy[j] = 0.0;
+  __syncthreads(); /* barriers initialised, y factors staged */
+
+  /* ---- 2. the rows that need no halo: [m0, m1); ring rows lo .. hi */
+  const int64_t m0 = jb + (ownS ? 1 : 0);
+  const int64_t m1 = je - (ownN ? 1 : 0);
+  if (m0 < m1)
+  {
+    const int64_t lo = (m0 > 0) ? m0 - 1 : 0;
+    const int64_t hi = (m1 < a.ny_loc) ? m1 : a.ny_loc - 1;
+    if (!consumer)
+    {
+      if (lane == 0)
+      {
+        /* the tile's span of a row, clipped to the mesh: [xs, xe) */
+        const int64_t xs     = (xt >= 2) ? xt - 2 : 0;
+        const int64_t xe     = (xt + kTX + 2 <= a.nx) ? xt + kTX + 2 : a.nx;
+        const uint32_t bytes = (uint32_t)((xe - xs) * sizeof(double));
+        const uint32_t doff  = (uint32_t)((xs - (xt - 2)) * sizeof(double));
+        asm volatile("fence.proxy.async;" ::: "memory");
+        for (int64_t r = lo; r <= hi; r++)
+        {
+          const int64_t i = r - lo;
+          const int st    = (int)(i % kStages);
+          if (i >= kStages) mbar_wait(bar_empty + 8 * st, (uint32_t)((i / kStages - 1) & 1));
+          mbar_expect_tx(bar_full + 8 * st, bytes);
+          bulk_g2s(smem_addr(ring + (size_t)st * kRowDbl) + doff, a.u + r * a.nx + xs, bytes, bar_full + 8 * st);
+        }
+      }
+    }
+    else
+    {
+      const int px = 2 + tid * W; /* this thread's first point inside a stage */
+      double s[W], c[W], n[W];
+#pragma unroll
+      for (int k = 0; k < W; k++) s[k] = c[k] = n[k] = 0.0;
+      if (m0 > lo) /* south of the first row */
+      {
+        mbar_wait(bar_full + 0, 0);
+        lds4(ring + px, s);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 0);
+      }
+      const double* pc;
+      {
+        const int64_t i = m0 - lo;
+        const int st    = (int)(i % kStages);
+        mbar_wait(bar_full + 8 * st, (uint32_t)((i / kStages) & 1));
+        pc = ring + (size_t)st * kRowDbl;
+        lds4(pc + px, c);
+      }
+      for (int64_t j = m0; j < m1; j++)
+      {
+        const double* pn = pc;
+        if (j + 1 <= hi)
+        {
+          const int64_t i = j + 1 - lo;
+          const int st    = (int)(i % kStages);
+          mbar_wait(bar_full + 8 * st, (uint32_t)((i / kStages) & 1));
+          pn = ring + (size_t)st * kRowDbl;
+          lds4(pn + px, n);
+        }
+        if (act)
+        {
+          const double w = pc[px - 1], e = pc[px + W];
+          stencil_store<W>(a, j, x0, s, c, n, w, e, s_sy[j - jb], s_dy[j - jb], tdcx, tssx);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * (int)((j - lo) % kStages)); /* row j served as centre: free it */
+#pragma unroll
+        for (int k = 0; k < W; k++)
+        {
+          s[k] = c[k];
+          c[k] = n[k];
+        }
+        pc = pn;
+      }
+    }
+  }
+
+  /* ---- 3. the halo-dependent rows, last (register path) */
+  if (ownN)
+  {
+    const int64_t j = a.ny_loc - 1;
+    Row<W> s, c, n;
+    s.edge = c.edge = n.edge = 0.0;
+    load_row<W>(a, j - 1, xo, x0, lane, s);
+    load_row<W>(a, j, xo, x0, lane, c);
+    wait_counter(a.ctrN_local, a.expected);
+    ld_halo<W>(a.recvN + xo, n.v);
+    compute_row<W>(a, j, x0, act, s.v, c, n.v, s_sy[j - jb], s_dy[j - jb], tdcx, tssx);
+  }
+  if (ownS)
+  {
+    Row<W> s, c, n;
+    s.edge = c.edge = n.edge = 0.0;
+    load_row<W>(a, 0, xo, x0, lane, c);
+    load_row<W>(a, 1, xo, x0, lane, n);
+    wait_counter(a.ctrS_local, a.expected);
+    ld_halo<W>(a.recvS + xo, s.v);
+    compute_row<W>(a, 0, x0, act, s.v, c, n.v, s_sy[0], s_dy[0], tdcx, tssx);
+  }
+}
+
 /* u = sin^2(pi x) sin^2(pi y) cos^2(pi t) inside, 0 on the boundary
    (mpi_serial/solution.cpp:25-62) */
 __global__ void __launch_bounds__(kThreads) k_solution(double* u, int64_t nx, int64_t ny, int64_t ny_loc, int64_t js,
@@ -340,7 +593,8 @@ const RhsVariant kVariants[] = {
 
 struct b200_diffusion2d_plan_s
 {
-  rhs_kernel_t kernel = nullptr;
+  rhs_kernel_t kernel = nullptr; /* register-march kernel (any nx, any alignment) */
+  bool use_tma        = false;   /* TMA ring kernel when nx % 4 == 0 and u is 16-byte aligned */
   b200vec_ctx ctx     = nullptr;
   b200_diffusion2d_opts o;
   int rank = 0, np = 1;
@@ -442,7 +696,19 @@ int b200_diffusion2d_plan_create(b200vec_ctx ctx, const b200_diffusion2d_opts* o
       for (const RhsVariant& v : kVariants)
         if (!strcmp(v.name, want)) var = &v;
     p->kernel = (p->W == 4) ? var->k4 : var->k1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->kernel, kThreads, 0);
+    const char* want = getenv("B200_DIFFUSION_VARIANT");
+    p->use_tma       = (p->W == 4) && (!want || !strcmp(want, "tma"));
+    if (p->use_tma)
+    {
+      if (cudaFuncSetAttribute(k_diffusion_rhs_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem) !=
+          cudaSuccess)
+      {
+        cudaGetLastError();
+        p->use_tma = false;
+      }
+    }
+    if (p->use_tma) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_diffusion_rhs_tma, kTmaThreads, kTmaSmem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->kernel, kThreads, 0);
     if (occ < 1) occ = 1;
     int64_t R = p->o.rows_per_cta;
     if (R <= 0)
@@ -452,7 +718,7 @@ int b200_diffusion2d_plan_create(b200vec_ctx ctx, const b200_diffusion2d_opts* o
       R = (p->ny_loc + blocks_y - 1) / blocks_y;
     }
     if (R < 2) R = 2;
-    if (R > kMaxRows) R = kMaxRows;
+    if (R > (p->use_tma ? kTmaRows : kMaxRows)) R = p->use_tma ? kTmaRows : kMaxRows;
     p->o.rows_per_cta = (int)R;
   }
 
@@ -565,7 +831,14 @@ int b200_diffusion2d_rhs(b200_diffusion2d_plan p, double t, const double* u, dou
   cfg.attrs                                        = at;
   cfg.numAttrs                                     = 1;
   if (p->time_rhs) cudaEventRecord(p->e0, s);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, p->kernel, a, R);
+  cudaError_t e;
+  if (p->use_tma && ((uintptr_t)u % 16 == 0) && ((uintptr_t)f % 32 == 0))
+  {
+    cfg.blockDim         = dim3(kTmaThreads);
+    cfg.dynamicSmemBytes = kTmaSmem;
+    e                    = cudaLaunchKernelEx(&cfg, k_diffusion_rhs_tma, a, R);
+  }
+  else e = cudaLaunchKernelEx(&cfg, p->kernel, a, R);
   if (e != cudaSuccess)
   {
     fprintf(stderr, "[diffusion2d_b200] RHS launch failed: %s\n", cudaGetErrorString(e));
