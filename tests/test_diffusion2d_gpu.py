@@ -97,10 +97,11 @@ def _close_to_reference(out, tag):
     want = (GOLD / f"{tag}.out").read_text()
     tg, tw = _table(_tail(out)), _table(_tail(want))
     assert len(tg) == len(tw)
+    scale = max(w[1] for w in tw)  # ||u||_rms passes through ~0 at t = 0.5: compare on the solution's scale
     for g, w in zip(tg, tw):
         assert abs(g[0] - w[0]) <= 1e-12
         # rtol 1e-5 / atol 1e-10 integration: two valid step sequences agree to ~1e-5
-        assert abs(g[1] - w[1]) <= 2e-5 * max(abs(w[1]), 1e-3), (g, w)
+        assert abs(g[1] - w[1]) <= 2e-5 * scale, (g, w)
         if len(w) == 3:
             assert abs(g[2] - w[2]) <= 0.05 * abs(w[2]) + 2e-6, (g, w)
     # the reference problem is solved with PCG capped at 20 iterations and Jacobi on a
