@@ -472,13 +472,21 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_diffusion_rhs_tma(const __gr
         const uint32_t bytes = (uint32_t)((xe - xs) * sizeof(double));
         const uint32_t doff  = (uint32_t)((xs - (xt - 2)) * sizeof(double));
         asm volatile("fence.proxy.async;" ::: "memory");
-        for (int64_t r = lo; r <= hi; r++)
+        int st = 0;             /* stage of row r and the parity of its previous use */
+        uint32_t par = 1;       /* flips each time the ring wraps; first pass: nothing to wait for */
+        bool wrapped = false;
+        const double* src = a.u + lo * a.nx + xs;
+        for (int64_t r = lo; r <= hi; r++, src += a.nx)
         {
-          const int64_t i = r - lo;
-          const int st    = (int)(i % kStages);
-          if (i >= kStages) mbar_wait(bar_empty + 8 * st, (uint32_t)((i / kStages - 1) & 1));
+          if (wrapped) mbar_wait(bar_empty + 8 * st, par);
           mbar_expect_tx(bar_full + 8 * st, bytes);
-          bulk_g2s(smem_addr(ring + (size_t)st * kRowDbl) + doff, a.u + r * a.nx + xs, bytes, bar_full + 8 * st);
+          bulk_g2s(smem_addr(ring + (size_t)st * kRowDbl) + doff, src, bytes, bar_full + 8 * st);
+          if (++st == kStages)
+          {
+            st      = 0;
+            par ^= 1u;
+            wrapped = true;
+          }
         }
       }
     }
@@ -488,30 +496,37 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_diffusion_rhs_tma(const __gr
       double s[W], c[W], n[W];
 #pragma unroll
       for (int k = 0; k < W; k++) s[k] = c[k] = n[k] = 0.0;
+      int st = 0;       /* stage and parity of the next row to take from the ring */
+      uint32_t par = 0;
+      auto next_row = [&]() -> const double* {
+        mbar_wait(bar_full + 8 * st, par);
+        const double* p = ring + (size_t)st * kRowDbl;
+        if (++st == kStages)
+        {
+          st = 0;
+          par ^= 1u;
+        }
+        return p;
+      };
+      int rel = 0; /* stage of the oldest row not yet released */
+      auto release = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * rel);
+        if (++rel == kStages) rel = 0;
+      };
       if (m0 > lo) /* south of the first row */
       {
-        mbar_wait(bar_full + 0, 0);
-        lds4(ring + px, s);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 0);
+        lds4(next_row() + px, s);
+        release();
       }
-      const double* pc;
-      {
-        const int64_t i = m0 - lo;
-        const int st    = (int)(i % kStages);
-        mbar_wait(bar_full + 8 * st, (uint32_t)((i / kStages) & 1));
-        pc = ring + (size_t)st * kRowDbl;
-        lds4(pc + px, c);
-      }
+      const double* pc = next_row();
+      lds4(pc + px, c);
       for (int64_t j = m0; j < m1; j++)
       {
         const double* pn = pc;
         if (j + 1 <= hi)
         {
-          const int64_t i = j + 1 - lo;
-          const int st    = (int)(i % kStages);
-          mbar_wait(bar_full + 8 * st, (uint32_t)((i / kStages) & 1));
-          pn = ring + (size_t)st * kRowDbl;
+          pn = next_row();
           lds4(pn + px, n);
         }
         if (act)
@@ -519,8 +534,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2) k_diffusion_rhs_tma(const __gr
           const double w = pc[px - 1], e = pc[px + W];
           stencil_store<W>(a, j, x0, s, c, n, w, e, s_sy[j - jb], s_dy[j - jb], tdcx, tssx);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * (int)((j - lo) % kStages)); /* row j served as centre: free it */
+        release(); /* row j served as centre: free its stage */
 #pragma unroll
         for (int k = 0; k < W; k++)
         {

@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=24)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--quick", action="store_true", help="dot/max-norm only: grid cap x PDL on/off, kernel-only and API")
     a = ap.parse_args()
     n = 1 << a.n
     ctx = nv.default_context()
@@ -36,6 +37,32 @@ def main():
         "wsqr_va8": (16 * nvv, lambda v: L.b200vec_wsqr_sum_vector_array(ctx.h, nvv, tab(v[:nvv]), tab(v[nvv:2 * nvv]), None, n, None)),
         "wsqr_mask_va8": (8 * (2 * nvv + 1), lambda v: L.b200vec_wsqr_sum_vector_array(ctx.h, nvv, tab(v[:nvv]), tab(v[nvv:2 * nvv]), v[2 * nvv].data_ptr(), n, None)),
     }
+    if a.quick:
+        out = C.c_double()
+        api = {
+            "dot_prod": (16, lambda v: L.b200vec_dot_prod(ctx.h, v[0].data_ptr(), v[1].data_ptr(), n, C.byref(out))),
+            "max_norm": (8, lambda v: L.b200vec_max_norm(ctx.h, v[0].data_ptr(), n, C.byref(out))),
+        }
+        for pdl in (1, 0):
+            ctx.set_tuning("pdl", pdl)
+            for mb in (148, 296, 444, 592, 888, 1184):
+                ctx.set_tuning("max_blocks", mb)
+                for mode, table in (("kernel", ops), ("api", api)):
+                    for name in ("dot_prod", "max_norm"):
+                        bpe, fn = table[name]
+                        for s in sets:
+                            fn(s)
+                        torch.cuda.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for r in range(a.reps):
+                            fn(sets[r % 3])
+                        e1.record()
+                        torch.cuda.synchronize()
+                        t = e0.elapsed_time(e1) / a.reps * 1e-3
+                        print(json.dumps({"op": name, "mode": mode, "pdl": pdl, "max_blocks": mb,
+                                          "us": round(t * 1e6, 2), "GBs": round(bpe * n / t / 1e9, 1)}), flush=True)
+        return
     grid = list(itertools.product([4, 2], [4, 2, 1], [148, 296, 592, 1184, 2368, 4096]))
     for name, (bpe, fn) in ops.items():
         best = None
