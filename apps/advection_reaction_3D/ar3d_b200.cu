@@ -1408,7 +1408,8 @@ extern "C" int b200_ar3d_run(b200vec_ctx ctx, const b200_ar3d_opts* opts, b200_a
       printf("   Total RHS evals: %li\n", st->nfi + d.nnlfi);
       printf("   Total number of error test failures = %li\n", st->netf);
       printf("   Total number of nonlinear solver convergence failures = %li\n", st->ncnf);
-      printf("   Total number of nonlinear iterations = %li\n", st->nni);
+      /* EvolveProblemAdams stops here (cvode_driver.cpp:315-320); BDF goes on (:163-170) */
+      if (o.method == AR3D_METHOD_CV_BDF) printf("   Total number of nonlinear iterations = %li\n", st->nni);
       if (newton)
       {
         printf("   Total number of linear iterations = %li\n", st->nli);

@@ -329,6 +329,55 @@ def run_diffusion_cpu_reference(n=2048, tf=1e-5):
             "ns_per_node_per_ls_iter": round(dt / max(nli, 1) / (n * n) * 1e9, 3)}
 
 
+def run_ar3d(ctx, world, args):
+    """Bounded solve of the re-hosted benchmarks/advection_reaction_3D (apps/advection_reaction_3D)
+    on the bench's own context: BASELINE config 5 -- npts^3 mesh (512^3 = 4.0e8 unknowns), slabs
+    in x over the ranks (STRONG scaling: the mesh is fixed), ARKODE IMEX-ARK order 3, Newton +
+    SPGMR with the reaction-block preconditioner, fused vector ops on."""
+    sys.path.insert(0, str(ROOT / "apps" / "advection_reaction_3D"))
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ar3d_run", ROOT / "apps" / "advection_reaction_3D" / "run.py")
+    app = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(app)
+    n = args.ar3d_npts
+    st = app.run(ctx, npts=n, method="ARK-IMEX", nls="newton", fused=1, tf=args.ar3d_tf, nout=1, output=0)
+    ev = st["evolve_seconds"]
+    return {
+        "workload": f"benchmarks/advection_reaction_3D re-host: {n}^3 mesh x 3 species = {st['neq']} unknowns, "
+                    f"slabs in x over {world} GPU(s) (strong scaling), ARKODE IMEX-ARK order 3, Newton + SPGMR + "
+                    f"block preconditioner, rtol 1e-6 atol 1e-9, fused ops, tf = {args.ar3d_tf} (bounded; the "
+                    f"benchmark's default is tf = 10)",
+        "scaling": "strong", "solve_s": round(ev, 4), "steps": st["nst"], "step_attempts": st["nst_a"],
+        "fe_evals": st["nfe"], "fi_evals": st["nfi"], "nls_iters": st["nni"], "ls_iters": st["nli"],
+        "prec_solves": st["npsol"], "ms_per_step": round(ev / max(st["nst"], 1) * 1e3, 3),
+        "ns_per_unknown_per_step": round(ev / max(st["nst"], 1) / st["neq"] * 1e9, 6),
+        "unknowns_per_gpu": st["neq_loc"], "urms": st["urms"], "vrms": st["vrms"], "wrms": st["wrms"],
+    }
+
+
+def run_ar3d_cpu_reference(n=64, tf=0.05):
+    """The reference's own benchmarks/advection_reaction_3D (RAJA sequential backend, one rank)
+    on a bounded sample: oracle/_ref/bin/advection_reaction_3D_ref."""
+    import re
+    import tempfile
+
+    exe = ROOT / "oracle" / "_ref" / "bin" / "advection_reaction_3D_ref"
+    if not exe.exists():
+        return {"unavailable": f"{exe} missing"}
+    with tempfile.TemporaryDirectory() as td:
+        t0 = time.perf_counter()
+        r = subprocess.run([str(exe), "--npts", str(n), "--method", "ARK-IMEX", "--nls", "newton", "--fused", "--tf",
+                            str(tf), "--nout", "1", "--dont-save", "--output-dir", td], capture_output=True, text=True,
+                           timeout=600, cwd=td)
+        dt = time.perf_counter() - t0
+    m = re.search(r"Internal solver steps = (\d+)", r.stdout)
+    nst = int(m.group(1)) if m else 0
+    return {"kind": "reference", "cores": 1, "sample": f"{n}^3 mesh, tf = {tf}, whole program wall time",
+            "wall_s": round(dt, 3), "steps": nst,
+            "ns_per_unknown_per_step": round(dt / max(nst, 1) / (3 * n ** 3) * 1e9, 3)}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -591,11 +640,25 @@ def b200_arm(args):
         except Exception as e:  # reported, never required for the op-suite line
             diffusion = {"unavailable": f"{type(e).__name__}: {e}"}
 
+    # ---- ARKODE advection_reaction_3D (BASELINE config 5); collective
+    ar3d = None
+    if not args.no_ar3d:
+        try:
+            ar3d = run_ar3d(ctx, world, args)
+        except Exception as e:
+            ar3d = {"unavailable": f"{type(e).__name__}: {e}"}
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
         return 0
+
+    if ar3d is not None and "solve_s" in ar3d and world == 1 and not args.no_cpu_baseline:
+        try:
+            ar3d["cpu_reference"] = run_ar3d_cpu_reference(tf=args.ar3d_tf)
+        except Exception as e:
+            ar3d["cpu_reference"] = {"unavailable": str(e)}
 
     if diffusion is not None and "solve_s" in diffusion and world == 1 and not args.no_cpu_baseline:
         try:
@@ -631,6 +694,7 @@ def b200_arm(args):
         "cpu_baseline": cpu,
         "clocks": clocks,
         "diffusion_2D": diffusion,
+        "advection_reaction_3D": ar3d,
         "per_op": per_op,
         "result_checksum": result_value,
         "ops_per_step": len(suite),
@@ -655,6 +719,9 @@ def main():
     ap.add_argument("--no-diffusion", action="store_true", help="skip the ARKODE diffusion_2D leg")
     ap.add_argument("--diffusion-n", type=int, default=8192, help="mesh points per GPU in x and y")
     ap.add_argument("--diffusion-tf", type=float, default=1e-4)
+    ap.add_argument("--no-ar3d", action="store_true", help="skip the ARKODE advection_reaction_3D leg")
+    ap.add_argument("--ar3d-npts", type=int, default=512, help="GLOBAL mesh points per direction")
+    ap.add_argument("--ar3d-tf", type=float, default=0.05)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
