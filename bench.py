@@ -648,6 +648,21 @@ def b200_arm(args):
         except Exception as e:
             ar3d = {"unavailable": f"{type(e).__name__}: {e}"}
 
+    # ---- Krylov Gram-Schmidt built on the ops: the reference's unmodified
+    # SUNClassicalGS / SUNModifiedGS on a basis of this vector; collective
+    gs = None
+    if not args.no_gs:
+        try:
+            sys.path.insert(0, str(ROOT / "tools"))
+            import gs_bench
+
+            gs = gs_bench.run(args.log2n, maxl=5, reps=5, cpu_log2n=args.cpu_log2n, with_ref_cuda=False,
+                              with_cpu=(world == 1 and not args.no_cpu_baseline), b200_ctx=ctx, rank=rank, world=world)
+            for k in ("classical", "modified"):
+                gs["b200"][k]["cycle_frac_of_peak"] = round(gs["b200"][k]["cycle_GBs"] / peak, 3)
+        except Exception as e:
+            gs = {"unavailable": f"{type(e).__name__}: {e}"}
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -695,6 +710,7 @@ def b200_arm(args):
         "clocks": clocks,
         "diffusion_2D": diffusion,
         "advection_reaction_3D": ar3d,
+        "gram_schmidt": gs,
         "per_op": per_op,
         "result_checksum": result_value,
         "ops_per_step": len(suite),
@@ -722,6 +738,7 @@ def main():
     ap.add_argument("--no-ar3d", action="store_true", help="skip the ARKODE advection_reaction_3D leg")
     ap.add_argument("--ar3d-npts", type=int, default=512, help="GLOBAL mesh points per direction")
     ap.add_argument("--ar3d-tf", type=float, default=0.05)
+    ap.add_argument("--no-gs", action="store_true", help="skip the Gram-Schmidt leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

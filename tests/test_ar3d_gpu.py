@@ -280,13 +280,15 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-def test_two_ranks_kernels_bit_exact_and_runs_match():
-    if _ngpus() < 2:
-        pytest.skip("needs 2 GPUs")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_n_ranks_kernels_bit_exact_and_runs_match(nproc):
+    """2 ranks: the periodic west and east neighbour are the same GPU; 4 ranks: they differ."""
+    if _ngpus() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
                         "--master-addr", "127.0.0.1", "--master-port", "29573", str(ROOT / "tests" / "ar3d_dist_gpu.py")],
                        capture_output=True, text=True, timeout=900, cwd=str(ROOT))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "AR3D DIST OK" in r.stdout
     for tag in ("imex_newton_8", "dirk_newton_8", "imex_newton_16", "dirk_newton_cneg_8"):
-        _close_to(_run(MANIFEST[tag]["args"], nproc=2, port=29575), (GOLD / f"{tag}.out").read_text(), count_rel=0.1)
+        _close_to(_run(MANIFEST[tag]["args"], nproc=nproc, port=29575), (GOLD / f"{tag}.out").read_text(), count_rel=0.1)

@@ -125,10 +125,13 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-def test_two_ranks_match_reference():
-    if _ngpus() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_n_ranks_match_reference(nproc):
+    """2 ranks: every strip has one neighbour; 4 ranks: the inner strips have a south AND a
+    north neighbour (both halo rows, both arrival counters in one launch)."""
+    if _ngpus() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
     # ranks own strips in y; global reductions are per-rank partials combined in rank
     # order, so the last bits differ from the single sequential sum
     for tag in ("default_32x32", "64x64_noforcing", "128x96_tf0.2"):
-        _close_to_reference(_run(MANIFEST[tag]["args"], nproc=2), tag)
+        _close_to_reference(_run(MANIFEST[tag]["args"], nproc=nproc), tag)

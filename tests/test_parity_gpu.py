@@ -140,3 +140,37 @@ def test_full_size_properties_2pow24(be):
     one = nv.N_VMake(torch.ones(n, dtype=torch.float64, device=dev), be.ctx)
     nv.N_VAbs(z, w)
     assert nv.N_VL1Norm(z) == nv.N_VDotProd(w, one)
+
+
+def test_length_2pow30_plus_ragged_tail_int64_indexing(be):
+    """The sweep's largest length (2^30 per GPU = 8 GiB per vector, byte offsets beyond 2^32 and
+    element indices beyond 2^30): exactly representable data with sentinels in the last tile,
+    so a 32-bit index or a dropped ragged tail changes an exact known answer."""
+    from sundials_b200 import nvector as nv
+
+    n = (1 << 30) + 5
+    free, _ = torch.cuda.mem_get_info()
+    if free < 4 * 8 * n + (2 << 30):
+        pytest.skip("needs ~34 GiB of free HBM")
+    dev = "cuda"
+    xt = torch.full((n,), 2.0, dtype=torch.float64, device=dev)
+    yt = torch.full((n,), 0.5, dtype=torch.float64, device=dev)
+    xt[n - 2] = -7.0          # in the scalar ragged tail
+    xt[(1 << 30) - 3] = 3.0   # in the last wide tile
+    x, y = nv.N_VMake(xt, be.ctx), nv.N_VMake(yt, be.ctx)
+    z = nv.N_VNew(n, be.ctx)
+    assert nv.N_VMaxNorm(x) == 7.0 and nv.N_VMin(x) == -7.0
+    assert nv.N_VL1Norm(x) == 2.0 * (n - 2) + 7.0 + 3.0
+    assert nv.N_VDotProd(x, y) == (n - 2) * 1.0 - 3.5 + 1.5
+    assert nv.N_VDotProdMulti(y, [x, y]) == [(n - 2) * 1.0 - 3.5 + 1.5, 0.25 * n]
+    nv.N_VLinearSum(3.0, x, -2.0, y, z)                      # 5 everywhere, -22 and 8 at the sentinels
+    assert float(z.data[n - 2]) == -22.0 and float(z.data[(1 << 30) - 3]) == 8.0 and float(z.data[n - 1]) == 5.0
+    assert nv.N_VL1Norm(z) == 5.0 * (n - 2) + 22.0 + 8.0
+    w = nv.N_VNew(n, be.ctx)
+    nv.N_VLinearCombination([1.0, 2.0, -1.0], [x, y, z], w)  # 2 + 1 - 5 = -2; sentinels: -7+1+22 = 16, 3+1-8 = -4
+    assert float(w.data[n - 2]) == 16.0 and float(w.data[(1 << 30) - 3]) == -4.0 and float(w.data[0]) == -2.0
+    assert nv.N_VL1Norm(w) == 2.0 * (n - 2) + 16.0 + 4.0
+    nv.N_VScaleAddMulti([2.0, -1.0], y, [x, z], [w, z])      # w = 2y + x, z = -y + z
+    assert float(w.data[n - 2]) == -6.0 and float(w.data[n - 1]) == 3.0
+    assert float(z.data[n - 2]) == -22.5 and float(z.data[n - 1]) == 4.5
+    assert nv.N_VMin(z) == -22.5
