@@ -82,6 +82,8 @@ struct ArArgs
   unsigned long long* ack_remote;        /* upstream neighbour's acknowledge counter                   */
   const unsigned long long* ack_local;   /* my acknowledge counter (bumped by my downstream neighbour) */
   unsigned long long ack_expected;       /* acknowledges that free this call's send buffer             */
+  unsigned long long* prof;              /* NULL, or the context's profile counters: [2],[3] ns / CTAs waiting for
+                                            the halo plane, [4],[5] ns / CTAs waiting for acknowledges           */
 };
 
 __device__ __forceinline__ void pdl_prologue()
@@ -142,12 +144,15 @@ __device__ __forceinline__ void st12(double* p, const double (&v)[12])
   st4(p + 8, v + 8);
 }
 
-__device__ __forceinline__ void wait_counter(const unsigned long long* ctr, unsigned long long expected)
+/* prof (optional, the context's profile counters): [0] += ns this CTA spun, [1] += 1 */
+__device__ __forceinline__ void wait_counter(const unsigned long long* ctr, unsigned long long expected,
+                                             unsigned long long* prof = nullptr)
 {
   if (threadIdx.x == 0)
   {
-    unsigned long long v, t0 = 0;
+    unsigned long long v, t0 = 0, p0 = 0;
     unsigned int spins = 0;
+    if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p0));
     for (;;)
     {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
@@ -159,6 +164,13 @@ __device__ __forceinline__ void wait_counter(const unsigned long long* ctr, unsi
         if (t0 == 0) t0 = now;
         else if (now - t0 > 30000000000ull) asm volatile("trap;"); /* dead neighbour: fail loudly, do not hang */
       }
+    }
+    if (prof)
+    {
+      unsigned long long p1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(p1));
+      atomicAdd(prof, p1 - p0);
+      atomicAdd(prof + 1, 1ull);
     }
   }
   __syncthreads();
@@ -309,7 +321,7 @@ __global__ void __launch_bounds__(kT, 3) k_ar3d_march(const __grid_constant__ Ar
 
   if (xch && ie == a.nxl)
   {
-    if (a.ack_expected) wait_counter(a.ack_local, a.ack_expected);
+    if (a.ack_expected) wait_counter(a.ack_local, a.ack_expected, a.prof ? a.prof + 4 : nullptr);
     if (act)
     {
       double v[12];
@@ -332,7 +344,7 @@ __global__ void __launch_bounds__(kT, 3) k_ar3d_march(const __grid_constant__ Ar
         march_plane<REACT>(a, i, P, m0, mj, me, need_edge, jface, kface0, act, prev, nullptr);
       }
     }
-    wait_counter(a.ctr_local, a.expected);
+    wait_counter(a.ctr_local, a.expected, a.prof ? a.prof + 2 : nullptr);
     march_plane<REACT>(a, 0, P, m0, mj, me, need_edge, jface, kface0, act, prev, a.halo);
     signal_counter(a.ack_remote);
   }
@@ -875,6 +887,8 @@ int b200_ar3d_rhs(b200_ar3d_plan p, int which, const double* y, double* f)
       a.ack_expected = p->acks_by_parity[par];
       p->acks += per_call;
       p->acks_by_parity[par] = p->acks;
+      if (b200vec_ctx_get_tuning(p->ctx, "profile") > 0)
+        a.prof = (unsigned long long*)(uintptr_t)b200vec_ctx_get_tuning(p->ctx, "prof_counters_ptr");
     }
     else a.halo = y + (int64_t)((a.dir > 0) ? p->nxl - 1 : 0) * p->plane;
     if (fast)

@@ -198,6 +198,9 @@ def main():
     ap.add_argument("--exact-threshold", type=int, default=None,
                     help="vector length up to which reductions sum in serial order (<= 4096)")
     ap.add_argument("--json", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="device-side wait times of the cross-rank exchanges (reductions, halo, acknowledges), per rank")
+    ap.add_argument("--p2p", type=int, default=None, help="0: ncclAllReduce after the reduction kernel instead of peer memory")
     a = ap.parse_args()
 
     import torch
@@ -219,10 +222,25 @@ def main():
         from sundials_b200 import _lib
 
         _lib.check(_lib.load().b200vec_ctx_set_tuning(ctx, b"exact_threshold", a.exact_threshold), "set_tuning")
+    if a.profile or a.p2p is not None:
+        from sundials_b200 import _lib
+
+        L = _lib.load()
+        if a.p2p is not None:
+            _lib.check(L.b200vec_ctx_set_tuning(ctx, b"p2p", a.p2p), "set_tuning(p2p)")
+        if a.profile:
+            _lib.check(L.b200vec_ctx_set_tuning(ctx, b"profile", 1), "set_tuning(profile)")
     st = run(ctx, npts=a.npts, xmax=a.xmax, A=a.A, B=a.B, k=a.k, c=a.c, method=a.method, nls=a.nls, order=a.order,
              fpaccel=a.fpaccel, precond=0 if a.nopre else 1, fused=1 if a.fused else 0, tf=a.tf, rtol=a.rtol,
              atol=a.atol, nout=a.nout, save=1 if a.save else 0, outputdir=a.output_dir, output=0 if a.quiet else 1,
              force_generic=1 if a.generic else 0, planes_per_cta=a.planes_per_cta)
+    if a.profile:
+        g = lambda i: L.b200vec_ctx_get_tuning(ctx, f"prof_counter_{i}".encode())  # noqa: E731
+        print("PROFILE " + json.dumps({
+            "rank": rank, "nranks": world, "evolve_s": round(st["evolve_seconds"], 4), "steps": st["nst"],
+            "reduction_exchange_ms": round(g(0) / 1e6, 3), "reduction_exchanges": g(1),
+            "halo_wait_ms_summed_over_ctas": round(g(2) / 1e6, 3), "halo_waiting_ctas": g(3),
+            "ack_wait_ms_summed_over_ctas": round(g(4) / 1e6, 3), "ack_waiting_ctas": g(5)}), file=sys.stderr, flush=True)
     if a.json and rank == 0:
         print(json.dumps(st), flush=True)
     if world > 1:

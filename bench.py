@@ -208,6 +208,57 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class LegSampler:
+    """nvidia-smi over ALL GPUs of the box while one integrator leg runs (rank 0 only): per GPU
+    the median / minimum SM clock, the peak power draw and the throttle reasons seen -- an
+    integrator leg advances at the pace of its slowest rank, so one capped GPU shows here."""
+    Q = "index," + ClockSampler.Q
+
+    def __init__(self):
+        self.rows, self.proc = [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self, ngpus):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        per = {}
+        for r in self.rows:
+            try:
+                g, sm, pw = int(r[0]), float(r[1]), float(r[3])
+            except (ValueError, IndexError):
+                continue
+            if g >= ngpus:
+                continue
+            d = per.setdefault(g, {"sm": [], "pw": 0.0, "reasons": set()})
+            d["sm"].append(sm)
+            d["pw"] = max(d["pw"], pw)
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    d["reasons"].add(name)
+        out = {}
+        for g, d in sorted(per.items()):
+            sm = sorted(d["sm"])
+            out[f"gpu{g}"] = {"sm_mhz_median": sm[len(sm) // 2], "sm_mhz_min": sm[0], "power_w_max": d["pw"],
+                              "reasons": sorted(d["reasons"]), "samples": len(sm)}
+        return out
+
+
 # --------------------------------------------------------------------------
 # reference CPU arm (the one place bench.py executes oracle/_ref)
 # --------------------------------------------------------------------------
@@ -635,18 +686,24 @@ def b200_arm(args):
     # ---- ARKODE diffusion_2D solve time (second half of BASELINE's metric); collective
     diffusion = None
     if not args.no_diffusion:
+        leg = LegSampler().start() if rank == 0 else None
         try:
             diffusion = run_diffusion(ctx, world, args)
         except Exception as e:  # reported, never required for the op-suite line
             diffusion = {"unavailable": f"{type(e).__name__}: {e}"}
+        if leg is not None:
+            diffusion["clocks"] = leg.stop(world)
 
     # ---- ARKODE advection_reaction_3D (BASELINE config 5); collective
     ar3d = None
     if not args.no_ar3d:
+        leg = LegSampler().start() if rank == 0 else None
         try:
             ar3d = run_ar3d(ctx, world, args)
         except Exception as e:
             ar3d = {"unavailable": f"{type(e).__name__}: {e}"}
+        if leg is not None:
+            ar3d["clocks"] = leg.stop(world)
 
     # ---- Krylov Gram-Schmidt built on the ops: the reference's unmodified
     # SUNClassicalGS / SUNModifiedGS on a basis of this vector; collective

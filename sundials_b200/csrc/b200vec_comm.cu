@@ -225,6 +225,7 @@ static void fill_xargs(b200vec_ctx ctx, XArgs* x)
   x->rank   = ctx->rank;
   x->seq    = ++ctx->xseq;
   if (x->seq == 0) x->seq = ++ctx->xseq; /* tag 0 is the "never written" value */
+  x->prof   = ctx->tune.profile ? ctx->d_prof : nullptr;
 }
 
 int take_scope(b200vec_ctx ctx, XArgs* x)
@@ -235,6 +236,7 @@ int take_scope(b200vec_ctx ctx, XArgs* x)
   x->nranks = 1;
   x->rank   = 0;
   x->seq    = 0;
+  x->prof   = nullptr;
   if (!global) return 0;
   if (ctx->p2p_ready && ctx->tune.p2p)
   {

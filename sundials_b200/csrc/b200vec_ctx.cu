@@ -80,6 +80,8 @@ int b200vec_ctx_create(b200vec_ctx* out, int device, void* stream)
   if (!rc) rc = check_cuda(cudaMemset(c->d_count, 0, sizeof(unsigned int) * kMaxRows), "cudaMemset(count)");
   if (!rc) rc = check_cuda(cudaMalloc((void**)&c->d_result, sizeof(double) * kMaxRows), "cudaMalloc(result)");
   if (!rc) rc = check_cuda(cudaMemset(c->d_result, 0, sizeof(double) * kMaxRows), "cudaMemset(result)");
+  if (!rc) rc = check_cuda(cudaMalloc((void**)&c->d_prof, sizeof(unsigned long long) * 8), "cudaMalloc(prof)");
+  if (!rc) rc = check_cuda(cudaMemset(c->d_prof, 0, sizeof(unsigned long long) * 8), "cudaMemset(prof)");
   if (!rc)
     rc = check_cuda(cudaHostAlloc((void**)&c->h_result, sizeof(double) * kHostSlots, cudaHostAllocMapped),
                     "cudaHostAlloc(result)");
@@ -115,6 +117,7 @@ int b200vec_ctx_release(b200vec_ctx ctx)
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_count) cudaFree(ctx->d_count);
   if (ctx->d_result) cudaFree(ctx->d_result);
+  if (ctx->d_prof) cudaFree(ctx->d_prof);
   if (ctx->d_commbuf) cudaFree(ctx->d_commbuf);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
   delete ctx;
@@ -200,6 +203,18 @@ int b200vec_ctx_set_tuning(b200vec_ctx ctx, const char* key, int64_t value)
   else if (!strcmp(key, "spin_wait")) ctx->tune.spin_wait = value ? 1 : 0;
   else if (!strcmp(key, "pdl")) ctx->tune.pdl = value ? 1 : 0;
   else if (!strcmp(key, "p2p")) ctx->tune.p2p = value ? 1 : 0;
+  else if (!strcmp(key, "profile"))
+  {
+    ctx->tune.profile = value ? 1 : 0;
+    DeviceGuard g(ctx->device);
+    int rc = check_cuda(cudaMemsetAsync(ctx->d_prof, 0, sizeof(unsigned long long) * 8, ctx->stream), "cudaMemset(prof)");
+    if (rc) return rc;
+  }
+  else if (!strcmp(key, "l2_prefetch"))
+  {
+    if (value < 0 || value > 4) return set_error(B200VEC_ERR_ARG, "l2_prefetch must be in [0,4]");
+    ctx->tune.l2_prefetch = value;
+  }
   else if (!strcmp(key, "count_launches"))
   {
     ctx->tune.count_launches = value ? 1 : 0;
@@ -221,6 +236,20 @@ int64_t b200vec_ctx_get_tuning(b200vec_ctx ctx, const char* key)
   if (!strcmp(key, "spin_wait")) return ctx->tune.spin_wait;
   if (!strcmp(key, "pdl")) return ctx->tune.pdl;
   if (!strcmp(key, "p2p")) return ctx->tune.p2p;
+  if (!strcmp(key, "l2_prefetch")) return ctx->tune.l2_prefetch;
+  if (!strcmp(key, "profile")) return ctx->tune.profile;
+  if (!strcmp(key, "prof_counters_ptr")) return (int64_t)(uintptr_t)ctx->d_prof;
+  if (!strncmp(key, "prof_counter_", 13))
+  {
+    /* prof_counter_<i>: synchronises the stream and reads counter i */
+    const int i = atoi(key + 13);
+    if (i < 0 || i >= 8) return -1;
+    DeviceGuard g(ctx->device);
+    unsigned long long v = 0;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, ctx->d_prof + i, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)v;
+  }
   return -1;
 }
 

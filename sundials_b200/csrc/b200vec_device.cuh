@@ -141,6 +141,8 @@ __device__ __forceinline__ double xrank_combine_warp(double v, int slot, const X
   const unsigned int par       = x.seq & 1u;
   const unsigned long long tag = (unsigned long long)x.seq << 32;
   double vq                    = C::identity();
+  unsigned long long prof_t0   = 0;
+  if (x.prof && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_t0));
   if (lane < x.nranks)
   {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
@@ -169,6 +171,13 @@ __device__ __forceinline__ double xrank_combine_warp(double v, int slot, const X
   }
   double acc = __shfl_sync(0xffffffffu, vq, 0);
   for (int q = 1; q < x.nranks; q++) acc = C::apply(acc, __shfl_sync(0xffffffffu, vq, q));
+  if (x.prof && lane == 0)
+  {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    atomicAdd(x.prof, t1 - prof_t0);
+    atomicAdd(x.prof + 1, 1ull);
+  }
   return acc;
 }
 

@@ -38,6 +38,11 @@ struct Tuning
   int64_t spin_wait       = 1; /* poll the pinned sequence word instead of cudaStreamSynchronize */
   int64_t p2p             = 1; /* global reductions exchange partials over NVLink peer memory inside
                                   the reduction kernel (0: ncclAllReduce after the kernel)         */
+  int64_t l2_prefetch     = 0; /* single-output reductions: tiles of cp.async.bulk.prefetch.L2 look-ahead per
+                                  CTA (0 = off); bytes in flight then do not depend on how many wide loads
+                                  ptxas keeps outstanding per thread                                       */
+  int64_t profile         = 0; /* accumulate device-side wait times of the cross-rank exchanges
+                                  (read back with get_tuning "prof_xwait_ns" / "prof_xwait_calls")        */
   int64_t pdl             = 1; /* programmatic dependent launch: a kernel's launch ramp overlaps the
                                   tail of its predecessor on the stream (griddepcontrol)          */
 };
@@ -60,6 +65,8 @@ struct XArgs
   int nranks;                          /* 1 = local reduction, no exchange                    */
   int rank;
   unsigned int seq; /* collective sequence number, identical on all ranks (SPMD) */
+  unsigned long long* prof; /* NULL, or the context's profile counters ("profile" tuning key):
+                               [0] ns spent between posting the own partial and having all peers', [1] calls */
 };
 } // namespace b200
 
@@ -75,6 +82,7 @@ struct b200vec_ctx_s
   double* d_partials    = nullptr; /* [kMaxOut][kMaxPartialBlocks]                 */
   unsigned int* d_count = nullptr; /* [kMaxRows] last-block-done tickets, self-resetting */
   double* d_result      = nullptr; /* [kMaxRows] result slots                       */
+  unsigned long long* d_prof = nullptr; /* [8] profile counters (XArgs::prof; apps add theirs from [2]) */
   /* pinned + mapped host mirror of the result slots: the final pass of every
      reduction kernel stores here directly, so a scalar-returning op costs one
      stream sync and no memcpy */

@@ -213,9 +213,24 @@ __device__ __forceinline__ void finish_block(double v, double* partials, unsigne
   combine_and_publish<C>(a, o, x);
 }
 
+/* one CTA tile (TILE doubles of every input operand) -> L2, issued by 4 threads of the CTA as
+   4 bulk prefetches per operand: the DRAM fetch of a later tile is in flight while the CTA
+   folds the current one, independently of how many wide loads ptxas keeps outstanding */
+template <int NIN, int64_t TILE>
+__device__ __forceinline__ void prefetch_tile_l2(const RedPtrs& p, int64_t tile)
+{
+  static_assert((TILE / 4 * 8) % 16 == 0, "bulk prefetch size is a multiple of 16 bytes");
+  if ((threadIdx.x & (kRBlock / 4 - 1)) != 0) return;
+  const int64_t off      = tile * TILE + (int64_t)(threadIdx.x / (kRBlock / 4)) * (TILE / 4);
+  constexpr uint32_t by  = (uint32_t)(TILE / 4 * 8);
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.p0 + off), "r"(by) : "memory");
+  if (NIN >= 2) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.p1 + off), "r"(by) : "memory");
+  if (NIN >= 3) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.p2 + off), "r"(by) : "memory");
+}
+
 template <int W, int U, class R>
 __global__ void __launch_bounds__(kRBlock)
-  k_reduce(R r, RedPtrs p, int64_t n, double* partials, unsigned int* counter, ResOut o, XArgs x)
+  k_reduce(R r, RedPtrs p, int64_t n, double* partials, unsigned int* counter, ResOut o, XArgs x, int pf)
 {
   using C = typename R::Comb;
   __shared__ double smem[kRBlock / 32];
@@ -223,13 +238,24 @@ __global__ void __launch_bounds__(kRBlock)
   constexpr int64_t STEP = (int64_t)kRBlock * W;
   const int64_t nfull    = n / TILE;
   pdl_prologue();
+  if (W < 2) pf = 0; /* bulk prefetch needs 16-byte aligned addresses */
 
   double acc[W];
 #pragma unroll
   for (int w = 0; w < W; w++) acc[w] = C::identity();
 
+  for (int d = 1; d < pf; d++)
+  {
+    const int64_t tn = (int64_t)blockIdx.x + (int64_t)d * gridDim.x;
+    if (tn < nfull) prefetch_tile_l2<R::NIN, TILE>(p, tn);
+  }
   for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
   {
+    if (pf > 0)
+    {
+      const int64_t tn = t + (int64_t)pf * gridDim.x;
+      if (tn < nfull) prefetch_tile_l2<R::NIN, TILE>(p, tn);
+    }
     const int64_t base = t * TILE + (int64_t)threadIdx.x * W;
     double a[U][W], b[U][W], c[U][W];
 #pragma unroll
@@ -414,7 +440,8 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
     const MapCfg c = pick_map_cfg(ctx, n, wmax, true, kRBlock);
 #define B200_RED_CASE(WW, UU)    \
   if (c.W == WW && c.U == UU)    \
-  launch_k(ctx, k_reduce<WW, UU, R>, dim3(c.grid), dim3(kRBlock), r, p, n, ctx->d_partials, ctx->d_count, out, xa)
+  launch_k(ctx, k_reduce<WW, UU, R>, dim3(c.grid), dim3(kRBlock), r, p, n, ctx->d_partials, ctx->d_count, out, xa, \
+           (int)ctx->tune.l2_prefetch)
     B200_RED_CASE(4, 4);
     else B200_RED_CASE(4, 2);
     else B200_RED_CASE(4, 1);

@@ -76,6 +76,27 @@ def test_every_kernel_geometry_gives_identical_streaming_bits(be, oracle, width,
         be.ctx.set_tuning("unroll", 0)
 
 
+@pytest.mark.parametrize("ahead", [1, 2])
+def test_reductions_with_l2_prefetch_lookahead(be, oracle, ahead):
+    """cp.async.bulk.prefetch.L2 look-ahead in the single-output reduction kernels moves no data
+    into registers: results must be the very same bits as without it (fixed tree), on aligned and
+    on 16-byte-aligned operands, and the written outputs of InvTest / ConstrMask stay bit-exact."""
+    from _b200_backend import B200Backend
+
+    n = (1 << 21) + 17
+    base = [fn(be, n, 31) for _, fn in reduction_cases()]
+    be.ctx.set_tuning("l2_prefetch", ahead)
+    try:
+        for (name, fn), want in zip(reduction_cases(), base):
+            got = fn(be, n, 31)
+            compare(f"{name}@prefetch={ahead}", got, want, exact_reductions=True, n=n, rtol=0.0)
+        _run_cases(reduction_cases(), be, oracle, n, 37, exact=False)
+        b2 = B200Backend(be.ctx, misalign=2)
+        _run_cases(reduction_cases(), b2, oracle, 300_001, 41, exact=False)
+    finally:
+        be.ctx.set_tuning("l2_prefetch", 0)
+
+
 def test_reductions_are_run_to_run_deterministic(be):
     from sundials_b200 import nvector as nv
 
