@@ -44,6 +44,16 @@ struct RDot
   static constexpr bool HAS_OUT = false;
   __device__ double term(double x, double y, double, double&, bool&) const { return x * y; }
 };
+/* x . x through ONE operand stream: Gram-Schmidt asks for N_VDotProd(v, v) once (classical) or
+   twice (modified) per column; reading v through both operand slots costs 16 B/elt of L2 traffic
+   for 8 B/elt of data.  Same products, same tile order: the same bits as RDot with y == x. */
+struct RSqr
+{
+  using Comb = CombSum;
+  static constexpr int NIN = 1;
+  static constexpr bool HAS_OUT = false;
+  __device__ double term(double x, double, double, double&, bool&) const { return x * x; }
+};
 struct RMaxNorm
 {
   using Comb = CombMax;
@@ -471,6 +481,8 @@ struct MultiArgs
   const double* A[kMaxOut];
   const double* B[kMaxOut];
   int nout;
+  int self_j; /* MODE 0: index j with A[j] == shared (classical Gram-Schmidt puts x itself into Y,
+                 sundials_iterative.c:135), -1 if none: that operand is not loaded a second time */
 };
 
 template <int MODE>
@@ -508,42 +520,65 @@ __device__ __forceinline__ void multi_combine_and_publish(double* s_fin, int nou
   if (threadIdx.x == 0) publish_done(o);
 }
 
-template <int W, int MODE>
+/* NO = outputs compiled in (2, 4 or 8; the launch's nout <= NO), U = tiles in flight per
+   thread.  Small output counts are what a GMRES cycle issues (classical Gram-Schmidt at column
+   k = 1..maxl is a (k+1)-wide multi-dot): with one tile per thread they would keep only
+   (1 + nout) x 32 B per thread outstanding on a few hundred resident threads -- too little to
+   cover HBM latency -- so the 2-output bucket unrolls two tiles and all small buckets, having
+   fewer accumulators and operands in registers, run more CTAs per SM (the grid is sized from
+   the occupancy of the instantiation). */
+template <int W, int MODE, int NO, int U>
 __global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__ MultiArgs m, int64_t n,
                                                          double* partials, unsigned int* counter, ResOut o, XArgs x)
 {
+  static_assert(NO <= kMaxOut, "outputs per launch");
   __shared__ double smem[kBlock / 32];
   __shared__ double s_fin[kMaxOut];
   __shared__ bool s_last;
-  constexpr int64_t TILE = (int64_t)kBlock * W;
+  constexpr int64_t STEP = (int64_t)kBlock * W;
+  constexpr int64_t TILE = STEP * U;
   const int64_t nfull    = n / TILE;
   const int nout         = m.nout;
+  const int self_j       = m.self_j;
 
-  double acc[kMaxOut];
+  double acc[NO];
 #pragma unroll
-  for (int j = 0; j < kMaxOut; j++) acc[j] = 0.0;
+  for (int j = 0; j < NO; j++) acc[j] = 0.0;
   pdl_prologue();
 
   for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
   {
     const int64_t base = t * TILE + (int64_t)threadIdx.x * W;
-    double sh[W], a[kMaxOut][W], b[kMaxOut][W];
-    if (MODE != 1) ldg<W>(m.shared + base, sh);
+    double sh[U][W], a[U][NO][W], b[U][NO][W];
 #pragma unroll
-    for (int j = 0; j < kMaxOut; j++)
-      if (j < nout)
-      {
-        ldg<W>(m.A[j] + base, a[j]);
-        if (MODE != 0) ldg<W>(m.B[j] + base, b[j]);
-      }
+    for (int u = 0; u < U; u++)
+    {
+      const int64_t off = base + u * STEP;
+      if (MODE != 1) ldg<W>(m.shared + off, sh[u]);
 #pragma unroll
-    for (int j = 0; j < kMaxOut; j++)
-      if (j < nout)
-      {
+      for (int j = 0; j < NO; j++)
+        if (j < nout)
+        {
+          /* every load of the tile is issued before any value is used; the self operand is
+             taken from sh at fold time (its a[u][j] stays unloaded and unselected) */
+          if (!(MODE == 0 && j == self_j)) ldg<W>(m.A[j] + off, a[u][j]);
+          if (MODE != 0) ldg<W>(m.B[j] + off, b[u][j]);
+        }
+    }
 #pragma unroll
-        for (int w = 0; w < W; w++)
-          acc[j] += multi_term<MODE>(MODE != 1 ? sh[w] : 0.0, a[j][w], MODE != 0 ? b[j][w] : 0.0);
-      }
+    for (int u = 0; u < U; u++)
+    {
+#pragma unroll
+      for (int j = 0; j < NO; j++)
+        if (j < nout)
+        {
+          const bool self = (MODE == 0 && j == self_j);
+#pragma unroll
+          for (int w = 0; w < W; w++)
+            acc[j] += multi_term<MODE>(MODE != 1 ? sh[u][w] : 0.0, self ? sh[u][w] : a[u][j][w],
+                                       MODE != 0 ? b[u][j][w] : 0.0);
+        }
+    }
   }
 
   const int64_t tail0 = nfull * TILE;
@@ -553,14 +588,14 @@ __global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__
     {
       const double sh = (MODE != 1) ? m.shared[i] : 0.0;
 #pragma unroll
-      for (int j = 0; j < kMaxOut; j++)
+      for (int j = 0; j < NO; j++)
         if (j < nout) acc[j] += multi_term<MODE>(sh, m.A[j][i], MODE != 0 ? m.B[j][i] : 0.0);
     }
   }
 
   /* CTA value of every output -> partials[j][block] (thread 0) */
 #pragma unroll
-  for (int j = 0; j < kMaxOut; j++)
+  for (int j = 0; j < NO; j++)
     if (j < nout)
     {
       const double v = block_combine<CombSum>(acc[j], smem);
@@ -620,6 +655,41 @@ __global__ void __launch_bounds__(kBlock)
   multi_combine_and_publish(s_fin, nout, o, x);
 }
 
+/* CTAs of one instantiation that fit an SM (registers decide: 8 outputs x 2 operand arrays in
+   256-bit form take ~170, the 2-output bucket ~70), asked once from the runtime */
+template <int W, int MODE, int NO, int U>
+static int multi_resident_ctas()
+{
+  static int nb = 0;
+  if (nb == 0)
+  {
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_reduce_multi<W, MODE, NO, U>, kBlock, 0) != cudaSuccess || v < 1)
+    {
+      (void)cudaGetLastError();
+      v = 1;
+    }
+    nb = (v > 4) ? 4 : v; /* 1024 threads per SM are plenty; keeps the partials rows short */
+  }
+  return nb;
+}
+
+/* persistent-style launch: exactly the resident CTA count of the instantiation (measured best for
+   these register-heavy kernels), fewer when the vector has fewer tiles */
+template <int W, int MODE, int NO, int U>
+static int launch_multi_cfg(b200vec_ctx ctx, const char* name, const MultiArgs& m, int64_t n, const ResOut& out,
+                            const XArgs& xa)
+{
+  int64_t tiles = n / ((int64_t)kBlock * W * U);
+  if (tiles < 1) tiles = 1;
+  int64_t cap = (int64_t)kSMs * multi_resident_ctas<W, MODE, NO, U>();
+  if (ctx->tune.max_blocks != kMaxBlocksDef && cap > ctx->tune.max_blocks) cap = ctx->tune.max_blocks; /* user override */
+  if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+  const int grid = (int)((tiles < cap) ? tiles : cap);
+  launch_k(ctx, k_reduce_multi<W, MODE, NO, U>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out, xa);
+  return check_launch(ctx, name);
+}
+
 template <int MODE>
 static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs& m, int64_t n, int slot0,
                               bool to_host, const XArgs& xa)
@@ -638,20 +708,21 @@ static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs
   }
   int W = wmax;
   if (ctx->tune.vec_width > 0 && ctx->tune.vec_width < W) W = (int)ctx->tune.vec_width;
-  int64_t tiles = n / ((int64_t)kBlock * W);
-  if (tiles < 1) tiles = 1;
-  /* register-heavy kernels (8 accumulators + 8..16 wide operands in flight): run
-     them persistent-style with exactly the resident CTA count -- 1 per SM for the
-     256-bit two-operand modes (~170 regs), 2 per SM otherwise -- measured best */
-  int64_t cap = (W == 4 && MODE != 0) ? kSMs : 2 * kSMs;
-  if (cap > ctx->tune.max_blocks) cap = ctx->tune.max_blocks;
-  const int grid = (int)((tiles < cap) ? tiles : cap);
-  if (W == 4)
-    launch_k(ctx, k_reduce_multi<4, MODE>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out, xa);
-  else if (W == 2)
-    launch_k(ctx, k_reduce_multi<2, MODE>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out, xa);
-  else launch_k(ctx, k_reduce_multi<1, MODE>, dim3(grid), dim3(kBlock), m, n, ctx->d_partials, ctx->d_count, out, xa);
-  return check_launch(ctx, name);
+  const int bucket = (m.nout <= 2) ? 2 : (m.nout <= 4) ? 4 : 8;
+#define B200_MULTI_CASE(WW, NN, UU)                                                                        \
+  if (W == WW && bucket == NN)                                                                             \
+  return launch_multi_cfg<WW, MODE, NN, UU>(ctx, name, m, n, out, xa)
+  B200_MULTI_CASE(4, 2, 2);
+  B200_MULTI_CASE(4, 4, 1);
+  B200_MULTI_CASE(4, 8, 1);
+  B200_MULTI_CASE(2, 2, 2);
+  B200_MULTI_CASE(2, 4, 1);
+  B200_MULTI_CASE(2, 8, 1);
+  B200_MULTI_CASE(1, 2, 2);
+  B200_MULTI_CASE(1, 4, 1);
+  B200_MULTI_CASE(1, 8, 1);
+#undef B200_MULTI_CASE
+  return set_error(B200VEC_ERR_ARG, "%s: no kernel for width %d", name, W);
 }
 
 /* nout outputs in groups of <= kMaxOut (<= fewer on the exact path so the
@@ -688,10 +759,12 @@ static int launch_multi(b200vec_ctx ctx, const char* name, int nout, const doubl
     MultiArgs m;
     m.shared = shared;
     m.nout   = (nout - j0 < group) ? nout - j0 : group;
+    m.self_j = -1;
     for (int j = 0; j < kMaxOut; j++)
     {
       m.A[j] = (j < m.nout) ? A[j0 + j] : nullptr;
       m.B[j] = (j < m.nout && B) ? B[j0 + j] : nullptr;
+      if (MODE == 0 && m.self_j < 0 && j < m.nout && shared && m.A[j] == shared) m.self_j = j;
     }
     if (j0 > 0 && scope == 1) next_xargs(ctx, &xa); /* every group is its own collective */
     int rc = launch_multi_group<MODE>(ctx, name, m, n, j0, to_host, xa);
@@ -714,6 +787,7 @@ extern "C" {
 int b200vec_dot_prod(b200vec_ctx ctx, const double* x, const double* y, int64_t n, double* result_host)
 {
   B200_RARGS(x && y);
+  if (x == y) return launch_reduce(ctx, "dot_prod(self)", RSqr{}, RedPtrs{x, nullptr, nullptr, nullptr}, n, 0.0, result_host);
   return launch_reduce(ctx, "dot_prod", RDot{}, RedPtrs{x, y, nullptr, nullptr}, n, 0.0, result_host);
 }
 

@@ -227,7 +227,7 @@ def fused_cases():
             mk(f"scale_add_multi[nv={nv},{alias}]", c_sam)
 
     # --- DotProdMulti (Y may contain x itself: classical Gram-Schmidt does that)
-    for nv in (1, 2, NVEC, 8, 9, 21):
+    for nv in (1, 2, 3, 4, NVEC, 8, 9, 21):   # 2 / 3-4 / 5-8 outputs are separate kernel instantiations
         def c_dpm(B, n, seed, nv=nv):
             rng = np.random.default_rng(seed)
             x = rng_vec(rng, n)
@@ -237,6 +237,19 @@ def fused_cases():
             return {"r:dots": np.asarray(d, dtype=np.float64).copy(),
                     "abs:dots": np.array([float(np.abs(x * y).sum()) for y in Y])}
         mk(f"dot_prod_multi[nv={nv}]", c_dpm)
+
+    # x itself at other positions of Y (the kernel reads it once, through the shared operand), twice, and absent
+    for (nv, pos) in ((2, (0,)), (3, (1,)), (4, (0, 3)), (6, (2,)), (10, (9,)), (4, ())):
+        def c_dpms(B, n, seed, nv=nv, pos=pos):
+            rng = np.random.default_rng(seed)
+            x = rng_vec(rng, n)
+            Y = [rng_vec(rng, n) for _ in range(nv)]
+            for p in pos:
+                Y[p] = x
+            d = B.dot_prod_multi(x, Y)
+            return {"r:dots": np.asarray(d, dtype=np.float64).copy(),
+                    "abs:dots": np.array([float(np.abs(x * y).sum()) for y in Y])}
+        mk(f"dot_prod_multi_self[nv={nv},pos={pos}]", c_dpms)
     return cases
 
 
@@ -275,7 +288,7 @@ def vector_array_cases():
             return {"rc": rc, **{f"z{j}": Z[j].copy() for j in range(nv)}}
         mk(f"const_va[nv={nv}]", c_cva)
 
-    for nv in (1, NVEC, 11):
+    for nv in (1, 2, 3, 4, NVEC, 11):
         def c_wva(B, n, seed, nv=nv):
             rng = np.random.default_rng(seed)
             X = [rng_vec(rng, n) for _ in range(nv)]
