@@ -593,18 +593,30 @@ __global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__
     }
   }
 
-  /* CTA value of every output -> partials[j][block] (thread 0) */
+  /* CTA value of every output -> partials[j][block].  All outputs share ONE barrier: every warp
+     folds its lanes per output by shuffle, lane 0 parks the NO warp values in shared memory, and
+     after the barrier thread j folds output j's kBlock/32 warp values in the fixed tree
+     ((w0+w4)+(w2+w6))+((w1+w5)+(w3+w7)) -- the order block_combine uses, so the bits are the same. */
+  static_assert(kBlock / 32 == 8, "warp-value tree below is written for 8 warps");
+  __shared__ double s_w[kMaxOut][kBlock / 32];
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < NO; j++)
-    if (j < nout)
-    {
-      const double v = block_combine<CombSum>(acc[j], smem);
-      if (threadIdx.x == 0)
+    for (int j = 0; j < NO; j++)
+      if (j < nout)
       {
-        if (gridDim.x == 1) s_fin[j] = v;
-        else partials[(size_t)j * kMaxPartialBlocks + blockIdx.x] = v;
+        const double v = warp_combine<CombSum>(acc[j]);
+        if (lane == 0) s_w[j][warp] = v;
       }
+    __syncthreads();
+    if (threadIdx.x < nout)
+    {
+      const double* w = s_w[threadIdx.x];
+      const double v  = ((w[0] + w[4]) + (w[2] + w[6])) + ((w[1] + w[5]) + (w[3] + w[7]));
+      if (gridDim.x == 1) s_fin[threadIdx.x] = v;
+      else partials[(size_t)threadIdx.x * kMaxPartialBlocks + blockIdx.x] = v;
     }
+  }
   if (gridDim.x == 1)
   {
     __syncthreads();
@@ -612,16 +624,25 @@ __global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__
     return;
   }
 
+  /* the partials were written by threads 0..nout-1: make them visible before thread 0 takes the
+     ticket (release) */
+  if (threadIdx.x < nout) __threadfence();
+  __syncthreads();
   if (threadIdx.x == 0) s_last = take_ticket(counter);
   __syncthreads();
   if (!s_last) return;
-  for (int j = 0; j < nout; j++)
+  /* last CTA: warp j folds output j's partials (lane-strided, then the shuffle tree) -- all outputs
+     at once instead of one block-wide pass per output; fixed order, so run-to-run identical */
   {
-    const double* row = partials + (size_t)j * kMaxPartialBlocks;
-    double a          = 0.0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) a += __ldcg(row + i);
-    a = block_combine<CombSum>(a, smem);
-    if (threadIdx.x == 0) s_fin[j] = a;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp < nout)
+    {
+      const double* row = partials + (size_t)warp * kMaxPartialBlocks;
+      double a          = 0.0;
+      for (unsigned int i = lane; i < gridDim.x; i += 32) a += __ldcg(row + i);
+      a = warp_combine<CombSum>(a);
+      if (lane == 0) s_fin[warp] = a;
+    }
   }
   if (threadIdx.x == 0) *counter = 0u;
   __syncthreads();
