@@ -532,7 +532,6 @@ __global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__
                                                          double* partials, unsigned int* counter, ResOut o, XArgs x)
 {
   static_assert(NO <= kMaxOut, "outputs per launch");
-  __shared__ double smem[kBlock / 32];
   __shared__ double s_fin[kMaxOut];
   __shared__ bool s_last;
   constexpr int64_t STEP = (int64_t)kBlock * W;
