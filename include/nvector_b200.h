@@ -64,6 +64,9 @@ N_Vector N_VNewPinned_B200(sunindextype length, SUNContext sunctx);
 /* explicit execution context (stream / workspace / communicator) and memory kind */
 N_Vector N_VNewWithCtx_B200(sunindextype length, int mem_kind, b200vec_ctx ctx, SUNContext sunctx);
 N_Vector N_VMake_B200(sunindextype length, sunrealtype* h_vdata, sunrealtype* d_vdata, SUNContext sunctx);
+/* wraps ONE user array that both sides can address (cudaMallocManaged / pinned-mapped memory), not
+   owned: N_VMakeManaged_Cuda, nvector_cuda.cu:387 */
+N_Vector N_VMakeManaged_B200(sunindextype length, sunrealtype* vdata, SUNContext sunctx);
 N_Vector N_VMakeWithCtx_B200(sunindextype length, sunrealtype* h_vdata, sunrealtype* d_vdata, b200vec_ctx ctx,
                              SUNContext sunctx);
 /* turn v (and its future clones) into the local block of a distributed vector;

@@ -283,6 +283,16 @@ N_Vector N_VMake_B200(sunindextype length, sunrealtype* h_vdata, sunrealtype* d_
   return N_VMakeWithCtx_B200(length, h_vdata, d_vdata, NULL, sunctx);
 }
 
+N_Vector N_VMakeManaged_B200(sunindextype length, sunrealtype* vdata, SUNContext sunctx)
+{
+  if (sunctx == NULL) return NULL;
+  if (length > 0 && vdata == NULL) return NULL;
+  /* h_vdata == d_vdata selects the host-coherent kind (cuda:387-437; here every op on it synchronises) */
+  N_Vector v = N_VMakeWithCtx_B200(length, vdata, vdata, NULL, sunctx);
+  if (v) NVC(v)->mem_kind = B200_MEM_MANAGED; /* also for length 0, where both pointers may be NULL */
+  return v;
+}
+
 SUNErrCode N_VMakeDistributed_B200(N_Vector v, sunindextype global_length)
 {
   if (!v || !v->content) return SUN_ERR_ARG_CORRUPT;
