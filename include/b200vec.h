@@ -99,6 +99,12 @@ int b200vec_free_managed(b200vec_ctx ctx, void* ptr);
 int b200vec_copy_h2d(b200vec_ctx ctx, void* dst_dev, const void* src_host, size_t bytes, int sync);
 int b200vec_copy_d2h(b200vec_ctx ctx, void* dst_host, const void* src_dev, size_t bytes, int sync);
 int b200vec_copy_d2d(b200vec_ctx ctx, void* dst_dev, const void* src_dev, size_t bytes);
+/* H2D on the context's own COPY stream (created on first use, non-blocking): starts once the work
+ * already issued on the ctx stream has finished (so a buffer still being read is not overwritten)
+ * and overlaps everything issued afterwards.  b200vec_copy_join makes the ctx stream wait for all
+ * copies issued so far -- an event wait on the device, the host does not block. */
+int b200vec_copy_h2d_async(b200vec_ctx ctx, void* dst_dev, const void* src_host, size_t bytes);
+int b200vec_copy_join(b200vec_ctx ctx);
 
 /* ------------------------------------------------------------------------
  * streaming ops (asynchronous on the ctx stream)
@@ -166,11 +172,18 @@ int b200vec_linear_combination(b200vec_ctx ctx, int nvec, const double* c_host, 
 /* Z_j = a_j x + Y_j, x read once; Y_j may alias Z_j.  serial:944-992 cuda:1424 */
 int b200vec_scale_add_multi(b200vec_ctx ctx, int nvec, const double* a_host, const double* x,
                             const double* const* Y, double* const* Z, int64_t n);
-/* d_j = sum_i x_i Y_j,i ; x read once per group of 8 outputs, full grid.
+/* d_j = sum_i x_i Y_j,i ; x read once per group of 24 outputs, full grid.
  * N_VDotProdMulti / N_VDotProdMultiLocal serial:994-1027 cuda:1489.
  * result_host as for the scalar reductions (nvec slots). */
 int b200vec_dot_prod_multi(b200vec_ctx ctx, int nvec, const double* x, const double* const* Y, int64_t n,
                            double* result_host);
+
+/* z = sum_j c_j X_j (as b200vec_linear_combination) AND result = sum_i z_i^2 of the values just
+ * written, in one kernel and one host round trip: the N_VLinearCombination + N_VDotProd(v[k], v[k])
+ * pair of a classical Gram-Schmidt step (src/sundials/sundials_iterative.c:137-152).  8 (nvec + 1)
+ * bytes per element instead of 8 (nvec + 1) + 8.  result_host as for the scalar reductions. */
+int b200vec_linear_combination_sqnorm(b200vec_ctx ctx, int nvec, const double* c_host, const double* const* X,
+                                      double* z, int64_t n, double* result_host);
 
 /* ------------------------------------------------------------------------
  * vector-array ops.  arrays_alias_* tell the launcher whether the reference

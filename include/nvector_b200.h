@@ -84,6 +84,10 @@ void N_VSetDeviceArrayPointer_B200(sunrealtype* d_vdata, N_Vector v);
 sunbooleantype N_VIsManagedMemory_B200(N_Vector v);
 void N_VCopyToDevice_B200(N_Vector v);
 void N_VCopyFromDevice_B200(N_Vector v);
+/* upload on the context's copy stream, overlapping the vector ops issued next; the context's
+ * stream waits for all pending uploads at N_VCopyJoin_B200 (stream-side wait, the host goes on) */
+void N_VCopyToDeviceAsync_B200(N_Vector v);
+void N_VCopyJoin_B200(N_Vector v);
 b200vec_ctx N_VGetCtx_B200(N_Vector v);
 /* all vectors sharing v's context move to `stream` (a cudaStream_t); replaces
  * N_VSetKernelExecPolicy_Cuda cuda:514 */
@@ -123,6 +127,9 @@ sunrealtype N_VMinQuotient_B200(N_Vector num, N_Vector denom);
 SUNErrCode N_VLinearCombination_B200(int nvec, sunrealtype* c, N_Vector* X, N_Vector z);
 SUNErrCode N_VScaleAddMulti_B200(int nvec, sunrealtype* a, N_Vector x, N_Vector* Y, N_Vector* Z);
 SUNErrCode N_VDotProdMulti_B200(int nvec, N_Vector x, N_Vector* Y, sunrealtype* dotprods);
+/* not an ops-table slot: z = sum c_i X_i and *sqnorm = z . z in ONE pass (used by
+ * SUNClassicalGS_B200, include/sundials_iterative_b200.h) */
+SUNErrCode N_VLinearCombinationSqNorm_B200(int nvec, sunrealtype* c, N_Vector* X, N_Vector z, sunrealtype* sqnorm);
 
 SUNErrCode N_VLinearSumVectorArray_B200(int nvec, sunrealtype a, N_Vector* X, sunrealtype b, N_Vector* Y,
                                         N_Vector* Z);

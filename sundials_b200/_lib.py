@@ -58,6 +58,8 @@ _SIGS = {
     "b200vec_copy_h2d": (_I, [ctx_t, _V, _V, C.c_size_t, _I]),
     "b200vec_copy_d2h": (_I, [ctx_t, _V, _V, C.c_size_t, _I]),
     "b200vec_copy_d2d": (_I, [ctx_t, _V, _V, C.c_size_t]),
+    "b200vec_copy_h2d_async": (_I, [ctx_t, _V, _V, C.c_size_t]),
+    "b200vec_copy_join": (_I, [ctx_t]),
     "b200vec_linear_sum": (_I, [ctx_t, _D, _V, _D, _V, _V, _L]),
     "b200vec_const": (_I, [ctx_t, _D, _V, _L]),
     "b200vec_prod": (_I, [ctx_t, _V, _V, _V, _L]),
@@ -81,6 +83,7 @@ _SIGS = {
     "b200vec_linear_combination": (_I, [ctx_t, _I, c_double_p, c_ptr_table, _V, _L]),
     "b200vec_scale_add_multi": (_I, [ctx_t, _I, c_double_p, _V, c_ptr_table, c_ptr_table, _L]),
     "b200vec_dot_prod_multi": (_I, [ctx_t, _I, _V, c_ptr_table, _L, c_double_p]),
+    "b200vec_linear_combination_sqnorm": (_I, [ctx_t, _I, c_double_p, c_ptr_table, _V, _L, c_double_p]),
     "b200vec_linear_sum_vector_array": (_I, [ctx_t, _I, _D, c_ptr_table, _D, c_ptr_table, c_ptr_table, _I, _I, _L]),
     "b200vec_scale_vector_array": (_I, [ctx_t, _I, c_double_p, c_ptr_table, c_ptr_table, _L]),
     "b200vec_const_vector_array": (_I, [ctx_t, _I, _D, c_ptr_table, _L]),

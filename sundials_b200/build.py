@@ -8,7 +8,7 @@ library exporting the C ABI of include/b200vec.h and include/nvector_b200.h.
 
 The C host layer needs the SUNDIALS public headers (struct layouts of
 N_Vector / N_Vector_Ops): by default the reference tree's include/ plus the
-configuration header generated into oracle/_ref/include by oracle/Makefile;
+configuration header generated into baseline/_ref/include by baseline/Makefile;
 override with SUNDIALS_INCLUDE="dir1:dir2" to build against an installed
 SUNDIALS.  If no headers are available (e.g. on the GPU box) and a prebuilt
 library exists, the prebuilt library is used as is.
@@ -32,7 +32,10 @@ LIBDIR = ROOT / "sundials_b200" / "lib"
 LIB = LIBDIR / "libsundials_nvecb200.so"
 
 CU_SOURCES = ["b200vec_ctx.cu", "b200vec_stream.cu", "b200vec_reduce.cu", "b200vec_fused.cu", "b200vec_comm.cu"]
-C_SOURCES = ["nvector_b200.c"]
+C_SOURCES = ["nvector_b200.c", "sundials_iterative_b200.c"]
+# separate tiny library: symbol interposition of SUNClassicalGS (see gs_interpose.c)
+GS_LIB = LIBDIR / "libsundials_b200gs.so"
+GS_SOURCES = ["gs_interpose.c"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -48,7 +51,7 @@ def sundials_includes() -> list[str]:
     env = os.environ.get("SUNDIALS_INCLUDE")
     if env:
         return [d for d in env.split(":") if d]
-    cands = [Path("/root/reference/include"), ROOT / "oracle" / "_ref" / "include"]
+    cands = [Path("/root/reference/include"), ROOT / "baseline" / "_ref" / "include"]
     return [str(c) for c in cands if c.exists()]
 
 
@@ -80,10 +83,10 @@ def _run(cmd: list[str], verbose: bool) -> str:
 def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     headers = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list(INC.glob("*.h"))
-    sources = [CSRC / s for s in CU_SOURCES + C_SOURCES]
+    sources = [CSRC / s for s in CU_SOURCES + C_SOURCES + GS_SOURCES]
     stamp = LIBDIR / ".build_digest"
     digest = _digest(headers + sources, " ".join(NVCC_FLAGS))
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+    if not force and LIB.exists() and GS_LIB.exists() and stamp.exists() and stamp.read_text() == digest:
         return LIB
     if not Path(nvcc).exists() or not have_sundials_headers():
         if LIB.exists():
@@ -91,7 +94,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             return LIB
         raise RuntimeError(
             "cannot build libsundials_nvecb200.so: need nvcc and the SUNDIALS headers "
-            "(run `make -C oracle ref` first, or set SUNDIALS_INCLUDE)"
+            "(run `make -C baseline` first, or set SUNDIALS_INCLUDE)"
         )
     OBJ.mkdir(parents=True, exist_ok=True)
     LIBDIR.mkdir(parents=True, exist_ok=True)
@@ -115,6 +118,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     # host link only (no relocatable device code): keeps the library pure sm_100a
     _run([gxx, "-shared", "-o", str(LIB), *objs, f"-L{cuda_lib}", "-lcudart_static", "-Wl,--no-undefined", "-ldl",
           "-lm", "-lpthread", "-lrt"], verbose)
+    # the interposer resolves SUNClassicalGS_B200 / N_VGetVectorID_B200 from the main library
+    _run([GCC, "-O2", "-std=gnu99", "-fPIC", "-shared", "-Wall", f"-I{INC}", *sun_inc, "-o", str(GS_LIB),
+          *[str(CSRC / s) for s in GS_SOURCES], f"-L{LIBDIR}", "-lsundials_nvecb200", "-Wl,-rpath,$ORIGIN", "-ldl"],
+         verbose)
     stamp.write_text(digest)
     return LIB
 

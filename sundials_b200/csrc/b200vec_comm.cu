@@ -224,7 +224,10 @@ static void fill_xargs(b200vec_ctx ctx, XArgs* x)
   x->nranks = ctx->nranks;
   x->rank   = ctx->rank;
   x->seq    = ++ctx->xseq;
-  if (x->seq == 0) x->seq = ++ctx->xseq; /* tag 0 is the "never written" value */
+  /* tag 0 is the "never written" value.  At the 32-bit wrap skip TWO values (0xffffffff -> 2) so that
+     consecutive collectives keep alternating mailbox halves (parity = seq & 1): skipping only 0 would
+     put two odd tags back to back and let a fast rank overwrite a slot a slower peer still polls. */
+  if (x->seq == 0) x->seq = ctx->xseq = 2;
   x->prof   = ctx->tune.profile ? ctx->d_prof : nullptr;
 }
 
@@ -236,7 +239,7 @@ int take_scope(b200vec_ctx ctx, XArgs* x)
   x->nranks = 1;
   x->rank   = 0;
   x->seq    = 0;
-  x->prof   = nullptr;
+  x->prof   = ctx->tune.profile ? ctx->d_prof : nullptr; /* also local reductions stamp start / publication */
   if (!global) return 0;
   if (ctx->p2p_ready && ctx->tune.p2p)
   {
@@ -255,14 +258,15 @@ __global__ void __launch_bounds__(kBlock) k_xrank(double* d_res, int count, XArg
 {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const int warp = threadIdx.x >> 5;
-  if (warp >= count) return;
-  const double v = d_res[warp];
-  double r;
-  if (OP == B200VEC_MAX) r = xrank_combine_warp<CombMax>(v, warp, x);
-  else if (OP == B200VEC_MIN) r = xrank_combine_warp<CombMin>(v, warp, x);
-  else r = xrank_combine_warp<CombSum>(v, warp, x);
-  if ((threadIdx.x & 31) == 0) d_res[warp] = r;
+  for (int j = threadIdx.x >> 5; j < count; j += kBlock / 32)
+  {
+    const double v = d_res[j];
+    double r;
+    if (OP == B200VEC_MAX) r = xrank_combine_warp<CombMax>(v, j, x);
+    else if (OP == B200VEC_MIN) r = xrank_combine_warp<CombMin>(v, j, x);
+    else r = xrank_combine_warp<CombSum>(v, j, x);
+    if ((threadIdx.x & 31) == 0) d_res[j] = r;
+  }
 }
 
 } // namespace b200

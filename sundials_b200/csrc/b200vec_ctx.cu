@@ -76,6 +76,12 @@ int b200vec_ctx_create(b200vec_ctx* out, int device, void* stream)
 
   rc = check_cuda(cudaMalloc((void**)&c->d_partials, sizeof(double) * kMaxOut * kMaxPartialBlocks),
                   "cudaMalloc(partials)");
+  if (!rc)
+    rc = check_cuda(cudaMalloc((void**)&c->d_tagged, sizeof(unsigned long long) * 2 * kMaxPartialBlocks),
+                    "cudaMalloc(tagged partials)");
+  if (!rc)
+    rc = check_cuda(cudaMemset(c->d_tagged, 0, sizeof(unsigned long long) * 2 * kMaxPartialBlocks),
+                    "cudaMemset(tagged partials)");
   if (!rc) rc = check_cuda(cudaMalloc((void**)&c->d_count, sizeof(unsigned int) * kMaxRows), "cudaMalloc(count)");
   if (!rc) rc = check_cuda(cudaMemset(c->d_count, 0, sizeof(unsigned int) * kMaxRows), "cudaMemset(count)");
   if (!rc) rc = check_cuda(cudaMalloc((void**)&c->d_result, sizeof(double) * kMaxRows), "cudaMalloc(result)");
@@ -111,10 +117,18 @@ int b200vec_ctx_release(b200vec_ctx ctx)
   if (--ctx->refcount > 0) return B200VEC_OK;
   DeviceGuard g(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream)
+  {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->ev_compute);
+    cudaEventDestroy(ctx->ev_copy);
+  }
   if (ctx->nccl_comm) b200vec_comm_finalize(ctx);
   for (auto& kv : ctx->cache) cudaFree(kv.second);
   ctx->cache.clear();
   if (ctx->d_partials) cudaFree(ctx->d_partials);
+  if (ctx->d_tagged) cudaFree(ctx->d_tagged);
   if (ctx->d_count) cudaFree(ctx->d_count);
   if (ctx->d_result) cudaFree(ctx->d_result);
   if (ctx->d_prof) cudaFree(ctx->d_prof);
@@ -208,6 +222,15 @@ int b200vec_ctx_set_tuning(b200vec_ctx ctx, const char* key, int64_t value)
     ctx->tune.profile = value ? 1 : 0;
     DeviceGuard g(ctx->device);
     int rc = check_cuda(cudaMemsetAsync(ctx->d_prof, 0, sizeof(unsigned long long) * 8, ctx->stream), "cudaMemset(prof)");
+    if (rc) return rc;
+  }
+  else if (!strcmp(key, "prof_stamp_reset"))
+  { /* arm the start/publish stamps of the next single-output reduction ([6] = min over CTAs) */
+    DeviceGuard g(ctx->device);
+    const unsigned long long init[2] = {~0ull, 0ull};
+    int rc = check_cuda(cudaMemcpyAsync(ctx->d_prof + 6, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream),
+                        "cudaMemcpy(prof stamps)");
+    if (!rc) rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
     if (rc) return rc;
   }
   else if (!strcmp(key, "l2_prefetch"))
@@ -348,6 +371,36 @@ int b200vec_copy_h2d(b200vec_ctx ctx, void* dst, const void* src, size_t bytes, 
   int rc = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync(H2D)");
   if (!rc && sync) rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
   return rc;
+}
+
+int b200vec_copy_h2d_async(b200vec_ctx ctx, void* dst, const void* src, size_t bytes)
+{
+  B200_CHECK_CTX(ctx);
+  if (bytes == 0) return B200VEC_OK;
+  DeviceGuard g(ctx->device);
+  int rc = B200VEC_OK;
+  if (!ctx->copy_stream)
+  {
+    rc = check_cuda(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate(copy)");
+    if (!rc) rc = check_cuda(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming), "cudaEventCreate");
+    if (!rc) rc = check_cuda(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming), "cudaEventCreate");
+    if (rc) return rc;
+  }
+  rc = check_cuda(cudaEventRecord(ctx->ev_compute, ctx->stream), "cudaEventRecord(compute)");
+  if (!rc) rc = check_cuda(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_compute, 0), "cudaStreamWaitEvent(copy)");
+  if (!rc) rc = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream), "cudaMemcpyAsync(H2D, copy stream)");
+  if (!rc) rc = check_cuda(cudaEventRecord(ctx->ev_copy, ctx->copy_stream), "cudaEventRecord(copy)");
+  if (!rc) ctx->copies_pending = true;
+  return rc;
+}
+
+int b200vec_copy_join(b200vec_ctx ctx)
+{
+  B200_CHECK_CTX(ctx);
+  if (!ctx->copies_pending) return B200VEC_OK;
+  DeviceGuard g(ctx->device);
+  ctx->copies_pending = false;
+  return check_cuda(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0), "cudaStreamWaitEvent(join)");
 }
 
 int b200vec_copy_d2h(b200vec_ctx ctx, void* dst, const void* src, size_t bytes, int sync)

@@ -19,12 +19,15 @@ constexpr int kRBlock       = 512;  /* threads per CTA of the single-output redu
 constexpr int kMaxBlocksDef = kSMs * 2; /* reductions: 2 CTAs x 512 threads per SM measured best
                                            (profiles/r01_mb_reduce_24b.txt) */
 constexpr int kMaxPartialBlocks = 4096; /* reduction partial rows (>= any max_blocks) */
-constexpr int kMaxOut       = 8;    /* outputs per multi-reduction launch             */
+constexpr int kMaxOut       = 24;   /* outputs per multi-reduction launch (GMRES maxl = 20 needs a 21-wide
+                                       classical Gram-Schmidt multi-dot, sunlinsol_spgmr.c:790)  */
+constexpr int kMaxPair      = 8;    /* outputs per launch of the two-operand-per-output modes (A_j, B_j pairs) */
 constexpr int kMaxRows      = 64;   /* result slots per context                       */
-constexpr int kFlagSlot     = kMaxRows;     /* pinned sequence word of multi-output reductions   */
-constexpr int kPairSlot     = kMaxRows + 2; /* pinned, 16-byte aligned {value, sequence} pair of
-                                               single-output reductions                         */
-constexpr int kHostSlots    = kMaxRows + 8;
+/* pinned host area: [0, kMaxRows) doubles = staging of b200vec_result_fetch; then 2 tagged 8-byte
+   words per result slot -- word = (sequence << 32) | 32 bits of the value -- which a reduction
+   kernel's final pass stores and the host polls.  Every 8-byte store is single-copy atomic on
+   PCIe and carries its own tag, so no fence and no separate flag is needed (NCCL-LL style). */
+constexpr int kHostSlots    = kMaxRows + 2 * kMaxRows;
 constexpr int kExactMaxElems = 4096; /* smem doubles available to the exact-order path */
 
 struct Tuning
@@ -66,7 +69,9 @@ struct XArgs
   int rank;
   unsigned int seq; /* collective sequence number, identical on all ranks (SPMD) */
   unsigned long long* prof; /* NULL, or the context's profile counters ("profile" tuning key):
-                               [0] ns spent between posting the own partial and having all peers', [1] calls */
+                               [0] ns spent between posting the own partial and having all peers', [1] calls;
+                               [6] %globaltimer of the earliest CTA of the last single-output reduction
+                               (atomicMin; the host resets it), [7] %globaltimer at its publication */
 };
 } // namespace b200
 
@@ -79,7 +84,9 @@ struct b200vec_ctx_s
   int64_t launches      = 0;
 
   /* reduction workspace (device) */
-  double* d_partials    = nullptr; /* [kMaxOut][kMaxPartialBlocks]                 */
+  double* d_partials    = nullptr; /* [kMaxOut][kMaxPartialBlocks]  (multi-output kernels, ticket scheme) */
+  unsigned long long* d_tagged = nullptr; /* [kMaxPartialBlocks][2] tagged CTA partials of the single-output
+                                      kernels: CTA 0 polls them, no ticket, no fence       */
   unsigned int* d_count = nullptr; /* [kMaxRows] last-block-done tickets, self-resetting */
   double* d_result      = nullptr; /* [kMaxRows] result slots                       */
   unsigned long long* d_prof = nullptr; /* [8] profile counters (XArgs::prof; apps add theirs from [2]) */
@@ -88,7 +95,13 @@ struct b200vec_ctx_s
      stream sync and no memcpy */
   double* h_result      = nullptr; /* host address   */
   double* h_result_dev  = nullptr; /* device alias   */
-  unsigned long long seq = 0;      /* reductions launched so far; word [kMaxRows] of h_result mirrors it */
+  unsigned long long seq = 0;      /* reductions launched so far; its low 32 bits tag the published words */
+
+  /* copy stream of b200vec_copy_h2d_async (lazily created) */
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_compute   = nullptr; /* "ctx stream reached this point": the copy stream waits for it */
+  cudaEvent_t ev_copy      = nullptr; /* "copies issued so far are done": b200vec_copy_join waits for it */
+  bool copies_pending      = false;
 
   /* exact-size free-list cache of device allocations (clone/destroy churn) */
   std::multimap<size_t, void*> cache;

@@ -31,6 +31,8 @@
  * HBM bytes per element: dot/wsqrsum 16, masked 24, maxnorm/min/l1 8,
  * invtest/minquotient 16, constrmask 24, multi-dot 8(nv+1).
  */
+#include <cstring>
+
 #include "b200vec_device.cuh"
 
 namespace b200 {
@@ -42,6 +44,8 @@ struct RDot
   using Comb = CombSum;
   static constexpr int NIN = 2;
   static constexpr bool HAS_OUT = false;
+  static constexpr bool NAN_HEAD = false;
+  static constexpr int MAXU = 4;
   __device__ double term(double x, double y, double, double&, bool&) const { return x * y; }
 };
 /* x . x through ONE operand stream: Gram-Schmidt asks for N_VDotProd(v, v) once (classical) or
@@ -52,6 +56,8 @@ struct RSqr
   using Comb = CombSum;
   static constexpr int NIN = 1;
   static constexpr bool HAS_OUT = false;
+  static constexpr bool NAN_HEAD = false;
+  static constexpr int MAXU = 4;
   __device__ double term(double x, double, double, double&, bool&) const { return x * x; }
 };
 struct RMaxNorm
@@ -59,6 +65,8 @@ struct RMaxNorm
   using Comb = CombMax;
   static constexpr int NIN = 1;
   static constexpr bool HAS_OUT = false;
+  static constexpr bool NAN_HEAD = false;
+  static constexpr int MAXU = 4;
   __device__ double term(double x, double, double, double&, bool&) const { return fabs(x); }
 };
 struct RMin
@@ -66,6 +74,8 @@ struct RMin
   using Comb = CombMin;
   static constexpr int NIN = 1;
   static constexpr bool HAS_OUT = false;
+  static constexpr bool NAN_HEAD = true;
+  static constexpr int MAXU = 4;
   __device__ double term(double x, double, double, double&, bool&) const { return x; }
 };
 struct RL1
@@ -73,6 +83,8 @@ struct RL1
   using Comb = CombSum;
   static constexpr int NIN = 1;
   static constexpr bool HAS_OUT = false;
+  static constexpr bool NAN_HEAD = false;
+  static constexpr int MAXU = 4;
   __device__ double term(double x, double, double, double&, bool&) const { return fabs(x); }
 };
 struct RWSqr
@@ -80,6 +92,8 @@ struct RWSqr
   using Comb = CombSum;
   static constexpr int NIN = 2;
   static constexpr bool HAS_OUT = false;
+  static constexpr bool NAN_HEAD = false;
+  static constexpr int MAXU = 4;
   __device__ double term(double x, double w, double, double&, bool&) const
   {
     const double p = x * w;
@@ -91,6 +105,8 @@ struct RWSqrMask
   using Comb = CombSum;
   static constexpr int NIN = 3;
   static constexpr bool HAS_OUT = false;
+  static constexpr bool NAN_HEAD = false;
+  static constexpr int MAXU = 4;
   __device__ double term(double x, double w, double id, double&, bool&) const
   {
     const double p = x * w;
@@ -103,6 +119,8 @@ struct RInvTest
   using Comb = CombMin;
   static constexpr int NIN = 1;
   static constexpr bool HAS_OUT = true;
+  static constexpr bool NAN_HEAD = false;
+  static constexpr int MAXU = 4;
   __device__ double term(double x, double, double, double& outv, bool& store) const
   {
     store = (x != 0.0);
@@ -115,6 +133,8 @@ struct RConstrMask
   using Comb = CombMin;
   static constexpr int NIN = 2;
   static constexpr bool HAS_OUT = true;
+  static constexpr bool NAN_HEAD = false;
+  static constexpr int MAXU = 2 /* fp64 division / predicate chain: two tiles in flight fit 64 registers */;
   __device__ double term(double c, double x, double, double& outv, bool& store) const
   {
     store          = true;
@@ -130,6 +150,8 @@ struct RMinQuot
   using Comb = CombMin;
   static constexpr int NIN = 2;
   static constexpr bool HAS_OUT = false;
+  static constexpr bool NAN_HEAD = false;
+  static constexpr int MAXU = 2 /* fp64 division / predicate chain: two tiles in flight fit 64 registers */;
   __device__ double term(double num, double den, double, double&, bool&) const
   {
     return (den == 0.0) ? DBL_MAX : num / den;
@@ -144,38 +166,35 @@ struct RedPtrs
   double* out;
 };
 
-/* where a finished reduction publishes its value(s): the context's device
-   slots and -- only when the host asked for the scalar(s), h_res != NULL -- their
-   pinned host mirror.  Single results travel as one 16-byte {value, seq} store
-   (one PCIe write, no system fence); multi results as values, system fence,
-   sequence word.  The host polls the sequence instead of paying a
-   cudaStreamSynchronize round trip. */
+/* where a finished reduction publishes its value(s): the context's device slots and -- only when
+   the host asked for the scalar(s), h_words != NULL -- two tagged 8-byte words per slot in pinned,
+   device-mapped host memory: word = (tag << 32) | 32 bits of the value.  Each 8-byte store is
+   single-copy atomic all the way across PCIe and carries its own tag, so there is no fence, no
+   separate flag and no reliance on 16-byte store atomicity; the host polls the words instead of
+   paying a cudaStreamSynchronize round trip. */
 struct ResOut
 {
   double* d_res;
-  double* h_res;  /* mapped pinned slots, or NULL: no host publication */
-  double* h_pair; /* mapped pinned {value, seq}, 16-byte aligned       */
-  volatile unsigned long long* h_flag;
-  unsigned long long seq;
+  unsigned long long* h_words; /* words of slot 0 of this launch, or NULL: no host publication */
+  unsigned int tag;            /* low 32 bits of the context's reduction sequence number       */
 };
 
-__device__ __forceinline__ void publish_single(const ResOut& o, double v)
+__device__ __forceinline__ void store_tagged(unsigned long long* dst, unsigned int tag, double v)
 {
-  *o.d_res = v;
-  if (o.h_res)
-    asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(o.h_pair), "d"(v), "d"(__longlong_as_double((long long)o.seq))
-                 : "memory");
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long t    = (unsigned long long)tag << 32;
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(t | (bits & 0xffffffffull)), "l"(t | (bits >> 32))
+               : "memory");
 }
 
-__device__ __forceinline__ void publish_done(const ResOut& o)
+__device__ __forceinline__ void publish_slot(const ResOut& o, int slot, double v)
 {
-  if (!o.h_res) return;
-  __threadfence_system(); /* results before the flag, all the way to host memory */
-  *o.h_flag = o.seq;
+  o.d_res[slot] = v;
+  if (o.h_words) store_tagged(o.h_words + 2 * slot, o.tag, v);
 }
 
-/* ticket of the last-block-done scheme: ONE acq_rel atomic releases this CTA's
-   partial(s) (written by the same thread) and acquires everybody else's */
+/* ticket of the last-block-done scheme (multi-output kernels): ONE acq_rel atomic releases this
+   CTA's partials and acquires everybody else's */
 __device__ __forceinline__ bool take_ticket(unsigned int* counter)
 {
   unsigned int t;
@@ -183,9 +202,16 @@ __device__ __forceinline__ bool take_ticket(unsigned int* counter)
   return t == gridDim.x - 1;
 }
 
+__device__ __forceinline__ unsigned long long global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 /* local value of this rank (valid in thread 0 of the calling CTA) -> optional
    cross-rank combine by warp 0 -> publication by thread 0.  Called by all
-   threads of ONE CTA (the last one, or the only one). */
+   threads of ONE CTA (the finishing one, or the only one). */
 template <class C>
 __device__ __forceinline__ void combine_and_publish(double a, const ResOut& o, const XArgs& x)
 {
@@ -195,31 +221,71 @@ __device__ __forceinline__ void combine_and_publish(double a, const ResOut& o, c
     a = __shfl_sync(0xffffffffu, a, 0);
     a = xrank_combine_warp<C>(a, 0, x);
   }
-  if (threadIdx.x == 0) publish_single(o, a);
+  if (threadIdx.x == 0)
+  {
+    publish_slot(o, 0, a);
+    if (x.prof) x.prof[7] = global_ns();
+  }
 }
 
-/* stage 2: executed by every CTA after it has its value in thread 0 */
-template <class C, int BLOCK>
-__device__ __forceinline__ void finish_block(double v, double* partials, unsigned int* counter, const ResOut& o,
-                                             const XArgs& x, double* smem)
+/* N_VMin starts from x[0] (serial:715-720): a NaN there is returned, a NaN anywhere else never
+   wins a strict comparison.  Mirrored here on the local block (on a distributed vector the fold
+   over ranks starts from rank 0's value, so the global result is serial's on the whole vector). */
+template <bool NANHEAD>
+__device__ __forceinline__ double nan_head(double a, const double* p0)
 {
-  __shared__ bool s_last;
+  if (NANHEAD)
+  {
+    const double h = *p0;
+    if (h != h) return h;
+  }
+  return a;
+}
+
+/* stage 2.  Every CTA has its value in thread 0 and stores it as a TAGGED pair into its slot of
+   the context's partials array; CTA 0 then polls the slots of all CTAs (tag == this launch's
+   sequence number) and folds them in fixed index order -- no ticket atomic, no fence, and the
+   finishing CTA is known in advance.  CTA 0 never waits for a CTA that has not been scheduled
+   while it holds resources that CTA needs beyond one CTA slot: every other CTA runs to completion
+   without waiting for anybody. */
+template <class C, int BLOCK, bool NANHEAD>
+__device__ __forceinline__ void finish_block(double v, unsigned long long* tagged, const ResOut& o, const XArgs& x,
+                                             double* smem, const double* p0)
+{
   if (gridDim.x == 1)
   {
+    if (threadIdx.x == 0) v = nan_head<NANHEAD>(v, p0);
     combine_and_publish<C>(v, o, x);
     return;
   }
-  if (threadIdx.x == 0)
-  {
-    partials[blockIdx.x] = v;
-    s_last               = take_ticket(counter);
-  }
-  __syncthreads();
-  if (!s_last) return;
+  if (threadIdx.x == 0 && blockIdx.x != 0) store_tagged(tagged + 2 * (size_t)blockIdx.x, o.tag, v);
+  if (blockIdx.x != 0) return;
   double a = C::identity();
-  for (unsigned int i = threadIdx.x; i < gridDim.x; i += BLOCK) a = C::apply(a, __ldcg(partials + i));
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += BLOCK)
+  {
+    if (i == 0)
+    {
+      a = C::apply(a, v); /* own value: thread 0 */
+      continue;
+    }
+    const unsigned long long* src = tagged + 2 * (size_t)i;
+    unsigned long long w0, w1, t0 = 0;
+    unsigned int spins = 0;
+    for (;;)
+    {
+      asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+      if ((unsigned int)(w0 >> 32) == o.tag && (unsigned int)(w1 >> 32) == o.tag) break;
+      if ((++spins & 0xfffu) == 0)
+      { /* a CTA of this grid that never reports is a lost launch: fail loudly, do not hang */
+        const unsigned long long now = global_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 30000000000ull) asm volatile("trap;");
+      }
+    }
+    a = C::apply(a, __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull))));
+  }
   a = block_combine<C, BLOCK>(a, smem);
-  if (threadIdx.x == 0) *counter = 0u; /* self-resetting for the next launch on this stream */
+  if (threadIdx.x == 0) a = nan_head<NANHEAD>(a, p0);
   combine_and_publish<C>(a, o, x);
 }
 
@@ -239,8 +305,8 @@ __device__ __forceinline__ void prefetch_tile_l2(const RedPtrs& p, int64_t tile)
 }
 
 template <int W, int U, class R>
-__global__ void __launch_bounds__(kRBlock)
-  k_reduce(R r, RedPtrs p, int64_t n, double* partials, unsigned int* counter, ResOut o, XArgs x, int pf)
+__global__ void __launch_bounds__(kRBlock, 2)
+  k_reduce(R r, RedPtrs p, int64_t n, unsigned long long* tagged, ResOut o, XArgs x, int pf)
 {
   using C = typename R::Comb;
   __shared__ double smem[kRBlock / 32];
@@ -248,6 +314,7 @@ __global__ void __launch_bounds__(kRBlock)
   constexpr int64_t STEP = (int64_t)kRBlock * W;
   const int64_t nfull    = n / TILE;
   pdl_prologue();
+  if (x.prof && threadIdx.x == 0) atomicMin(x.prof + 6, global_ns());
   if (W < 2) pf = 0; /* bulk prefetch needs 16-byte aligned addresses */
 
   double acc[W];
@@ -320,7 +387,7 @@ __global__ void __launch_bounds__(kRBlock)
 #pragma unroll
   for (int w = 1; w < W; w++) v = C::apply(v, acc[w]);
   v = block_combine<C, kRBlock>(v, smem);
-  finish_block<C, kRBlock>(v, partials, counter, o, x, smem);
+  finish_block<C, kRBlock, R::NAN_HEAD>(v, tagged, o, x, smem, p.p0);
 }
 
 /* exact-order path: one CTA, terms staged in shared memory, thread 0 folds
@@ -331,6 +398,7 @@ __global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, 
   using C = typename R::Comb;
   __shared__ double buf[kExactMaxElems];
   pdl_prologue();
+  if (x.prof && threadIdx.x == 0) atomicMin(x.prof + 6, global_ns());
   for (int i = threadIdx.x; i < n; i += kBlock)
   {
     double o;
@@ -344,6 +412,7 @@ __global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, 
   {
 #pragma unroll 8
     for (int i = 0; i < n; i++) a = C::apply(a, buf[i]);
+    if (n > 0) a = nan_head<R::NAN_HEAD>(a, p.p0);
   }
   combine_and_publish<C>(a, o, x);
 }
@@ -354,56 +423,59 @@ __global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, 
 static ResOut next_out(b200vec_ctx ctx, int slot0, bool to_host)
 {
   ResOut o;
-  o.d_res  = ctx->d_result + slot0;
-  o.h_res  = to_host ? ctx->h_result_dev + slot0 : nullptr;
-  o.h_pair = ctx->h_result_dev + kPairSlot;
-  o.h_flag = (volatile unsigned long long*)(ctx->h_result_dev + kFlagSlot);
-  o.seq    = ++ctx->seq;
+  ++ctx->seq;
+  o.d_res   = ctx->d_result + slot0;
+  o.h_words = to_host ? (unsigned long long*)(ctx->h_result_dev + kMaxRows) + 2 * slot0 : nullptr;
+  o.tag     = (unsigned int)ctx->seq;
   return o;
 }
 
-/* wait for the reduction launched last (sequence ctx->seq) and copy its `count`
-   pinned results.  packed: the single {value, seq} pair; else slots + flag. */
-static int finish_host(b200vec_ctx ctx, int count, double* result_host, bool packed)
+/* wait for the pinned words of result slots [0, count) to carry the tag of the reduction launched
+   last, then decode them.  The final pass stores them straight into pinned host memory: polling
+   costs ~1 us after the kernel's last store, a cudaStreamSynchronize round trip several times that.
+   Bounded spin, then fall back to the sync (which also surfaces asynchronous errors). */
+static int finish_host(b200vec_ctx ctx, int slot0, int count, double* result_host)
 {
   if (!result_host) return B200VEC_OK;
-  int rc    = B200VEC_OK;
-  bool seen = false;
-  volatile unsigned long long* flag =
-    (volatile unsigned long long*)(ctx->h_result + (packed ? kPairSlot + 1 : kFlagSlot));
-  const unsigned long long want = ctx->seq;
+  volatile unsigned long long* w = (volatile unsigned long long*)(ctx->h_result + kMaxRows) + 2 * slot0;
+  const unsigned int want        = (unsigned int)ctx->seq;
+  bool seen                      = false;
   if (ctx->tune.spin_wait)
   {
-    /* the final pass stores the scalar(s) and a sequence word into pinned host
-       memory: polling it costs ~1-2 us after the kernel ends, a
-       cudaStreamSynchronize round trip several times that.  Bounded spin, then
-       fall back to the sync (which also surfaces asynchronous errors). */
-    for (long spins = 0; spins < 20000000L; spins++)
+    for (long spins = 0; spins < 20000000L && !seen; spins++)
     {
-      if (*flag >= want)
-      {
-        seen = true;
-        break;
-      }
+      seen = true;
+      for (int i = 2 * count - 1; i >= 0; i--)
+        if ((unsigned int)(w[i] >> 32) != want)
+        {
+          seen = false;
+          break;
+        }
+      if (seen) break;
 #if defined(__x86_64__)
       __builtin_ia32_pause();
 #endif
       if ((spins & 0xffff) == 0xffff && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) break;
     }
   }
-  if (!seen) rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(reduction)");
-  if (rc) return rc;
+  if (!seen)
+  {
+    int rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(reduction)");
+    if (rc) return rc;
+    for (int i = 0; i < 2 * count; i++)
+      if ((unsigned int)(w[i] >> 32) != want)
+        return set_error(B200VEC_ERR_CUDA, "reduction finished without publishing result slot %d", i / 2);
+  }
   __atomic_thread_fence(__ATOMIC_ACQUIRE);
-  if (packed) result_host[0] = ((volatile double*)ctx->h_result)[kPairSlot];
-  else
-    for (int i = 0; i < count; i++) result_host[i] = ((volatile double*)ctx->h_result)[i];
+  for (int i = 0; i < count; i++)
+  {
+    const unsigned long long bits = (w[2 * i + 1] << 32) | (w[2 * i] & 0xffffffffull);
+    memcpy(result_host + i, &bits, sizeof(double));
+  }
   return B200VEC_OK;
 }
 
-int finish_reduction(b200vec_ctx ctx, int count, double* result_host)
-{
-  return finish_host(ctx, count, result_host, false);
-}
+int finish_reduction(b200vec_ctx ctx, int count, double* result_host) { return finish_host(ctx, 0, count, result_host); }
 
 /* global reduction without the peer transport: allreduce the device slots with
    NCCL on the same stream, then one fetch (nvector_manyvector.c:815 pattern) */
@@ -412,6 +484,15 @@ static int finish_global_nccl(b200vec_ctx ctx, int count, int op, double* result
   int rc = b200vec_allreduce(ctx, count, op);
   if (!rc && result_host) rc = b200vec_result_fetch(ctx, count, result_host);
   return rc;
+}
+
+/* grid of a single-output reduction: every CTA adds a slot to the finishing CTA's polling pass and
+   small vectors are latency-bound, so below 2^20 elements one CTA per SM at most */
+static int reduce_grid_cap(b200vec_ctx ctx, int64_t n)
+{
+  int64_t cap = ctx->tune.max_blocks;
+  if (cap == kMaxBlocksDef && n <= ((int64_t)1 << 20)) cap = kSMs;
+  return (int)cap;
 }
 
 template <class R>
@@ -447,10 +528,18 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
     wmax     = min(wmax, align_width(p.p1));
     wmax     = min(wmax, align_width(p.p2));
     wmax     = min(wmax, align_width(p.out));
-    const MapCfg c = pick_map_cfg(ctx, n, wmax, true, kRBlock);
+    MapCfg c = pick_map_cfg(ctx, n, wmax, true, kRBlock);
+    if (c.U > R::MAXU)
+    { /* keep the instantiation within 64 registers (2 CTAs x 512 threads per SM) */
+      c.U           = R::MAXU;
+      int64_t tiles = n / ((int64_t)kRBlock * c.W * c.U);
+      if (tiles < 1) tiles = 1;
+      c.grid = (int)((tiles < ctx->tune.max_blocks) ? tiles : ctx->tune.max_blocks);
+    }
+    c.grid = min(c.grid, reduce_grid_cap(ctx, n));
 #define B200_RED_CASE(WW, UU)    \
   if (c.W == WW && c.U == UU)    \
-  launch_k(ctx, k_reduce<WW, UU, R>, dim3(c.grid), dim3(kRBlock), r, p, n, ctx->d_partials, ctx->d_count, out, xa, \
+  launch_k(ctx, k_reduce<WW, UU, R>, dim3(c.grid), dim3(kRBlock), r, p, n, ctx->d_tagged, out, xa, \
            (int)ctx->tune.l2_prefetch)
     B200_RED_CASE(4, 4);
     else B200_RED_CASE(4, 2);
@@ -466,20 +555,20 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
   int rc = check_launch(ctx, name);
   if (rc) return rc;
   if (scope == 2) return finish_global_nccl(ctx, 1, C::op, result_host);
-  return finish_host(ctx, 1, result_host, true);
+  return finish_host(ctx, 0, 1, result_host);
 }
 
 /* ------------------------------------------------------ multi-output family
  * MODE 0: d_j = sum x * A_j            (DotProdMulti; shared = x)
  * MODE 1: d_j = sum (A_j * B_j)^2      (WrmsNormVectorArray)
  * MODE 2: same, masked by shared > 0   (WrmsNormMaskVectorArray; shared = id)
- * Up to kMaxOut outputs per launch; the shared operand is read once per
- * element and every A_j/B_j exactly once. */
+ * Up to kMaxOut (MODE 0) / kMaxPair (MODE 1, 2) outputs per launch; the shared operand is read
+ * once per element and every A_j/B_j exactly once. */
 struct MultiArgs
 {
   const double* shared;
   const double* A[kMaxOut];
-  const double* B[kMaxOut];
+  const double* B[kMaxPair];
   int nout;
   int self_j; /* MODE 0: index j with A[j] == shared (classical Gram-Schmidt puts x itself into Y,
                  sundials_iterative.c:135), -1 if none: that operand is not loaded a second time */
@@ -494,44 +583,40 @@ __device__ __forceinline__ double multi_term(double sh, double a, double b)
   return (sh > 0.0) ? p * p : 0.0;
 }
 
-/* s_fin[0..nout): this rank's values (visible to the whole CTA).  Warp j folds
-   output j across ranks (kBlock/32 == kMaxOut warps), then threads j < nout
-   store, thread 0 publishes.  Called by ALL threads of one CTA. */
+/* s_fin[0..nout): this rank's values (visible to the whole CTA).  Warp w folds outputs w, w + 8, ..
+   across ranks, then threads j < nout publish slot j (device slot + tagged pinned words).
+   Called by ALL threads of one CTA. */
 __device__ __forceinline__ void multi_combine_and_publish(double* s_fin, int nout, const ResOut& o, const XArgs& x)
 {
-  static_assert(kBlock / 32 >= kMaxOut, "one warp per output");
   if (x.nranks > 1)
   {
     const int warp = threadIdx.x >> 5;
-    if (warp < nout)
+    for (int j = warp; j < nout; j += kBlock / 32)
     {
-      const double v = xrank_combine_warp<CombSum>(s_fin[warp], warp, x);
+      const double v = xrank_combine_warp<CombSum>(s_fin[j], j, x);
       __syncwarp();
-      if ((threadIdx.x & 31) == 0) s_fin[warp] = v;
+      if ((threadIdx.x & 31) == 0) s_fin[j] = v;
     }
     __syncthreads();
   }
-  if (threadIdx.x < nout)
-  {
-    o.d_res[threadIdx.x] = s_fin[threadIdx.x];
-    if (o.h_res) o.h_res[threadIdx.x] = s_fin[threadIdx.x];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) publish_done(o);
+  if (threadIdx.x < nout) publish_slot(o, threadIdx.x, s_fin[threadIdx.x]);
 }
 
-/* NO = outputs compiled in (2, 4 or 8; the launch's nout <= NO), U = tiles in flight per
+/* NO = outputs compiled in (2, 4, 8, 16 or 24; the launch's nout <= NO), U = tiles in flight per
    thread.  Small output counts are what a GMRES cycle issues (classical Gram-Schmidt at column
    k = 1..maxl is a (k+1)-wide multi-dot): with one tile per thread they would keep only
    (1 + nout) x 32 B per thread outstanding on a few hundred resident threads -- too little to
    cover HBM latency -- so the 2-output bucket unrolls two tiles and all small buckets, having
    fewer accumulators and operands in registers, run more CTAs per SM (the grid is sized from
-   the occupancy of the instantiation). */
+   the occupancy of the instantiation).  Beyond 8 outputs the operands are loaded in batches of 8
+   while the shared operand's tile stays in registers: x is still read once for all of them. */
 template <int W, int MODE, int NO, int U>
 __global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__ MultiArgs m, int64_t n,
                                                          double* partials, unsigned int* counter, ResOut o, XArgs x)
 {
-  static_assert(NO <= kMaxOut, "outputs per launch");
+  static_assert(NO <= kMaxOut && (MODE == 0 || NO <= kMaxPair), "outputs per launch");
+  constexpr int NB = (NO < 8) ? NO : 8; /* operands whose loads are in flight together */
+  static_assert(NO % NB == 0, "whole batches");
   __shared__ double s_fin[kMaxOut];
   __shared__ bool s_last;
   constexpr int64_t STEP = (int64_t)kBlock * W;
@@ -548,35 +633,42 @@ __global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__
   for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
   {
     const int64_t base = t * TILE + (int64_t)threadIdx.x * W;
-    double sh[U][W], a[U][NO][W], b[U][NO][W];
+    double sh[U][W];
 #pragma unroll
     for (int u = 0; u < U; u++)
+      if (MODE != 1) ldg<W>(m.shared + base + u * STEP, sh[u]);
+#pragma unroll
+    for (int j0 = 0; j0 < NO; j0 += NB)
     {
-      const int64_t off = base + u * STEP;
-      if (MODE != 1) ldg<W>(m.shared + off, sh[u]);
+      double a[U][NB][W], b[U][NB][W];
 #pragma unroll
-      for (int j = 0; j < NO; j++)
-        if (j < nout)
-        {
-          /* every load of the tile is issued before any value is used; the self operand is
-             taken from sh at fold time (its a[u][j] stays unloaded and unselected) */
-          if (!(MODE == 0 && j == self_j)) ldg<W>(m.A[j] + off, a[u][j]);
-          if (MODE != 0) ldg<W>(m.B[j] + off, b[u][j]);
-        }
-    }
+      for (int u = 0; u < U; u++)
+      {
+        const int64_t off = base + u * STEP;
 #pragma unroll
-    for (int u = 0; u < U; u++)
-    {
+        for (int jj = 0; jj < NB; jj++)
+          if (j0 + jj < nout)
+          {
+            /* every load of the batch is issued before any value is used; the self operand is
+               taken from sh at fold time (its a[u][jj] stays unloaded and unselected) */
+            if (!(MODE == 0 && j0 + jj == self_j)) ldg<W>(m.A[j0 + jj] + off, a[u][jj]);
+            if (MODE != 0) ldg<W>(m.B[(j0 + jj) % kMaxPair] + off, b[u][jj]);
+          }
+      }
 #pragma unroll
-      for (int j = 0; j < NO; j++)
-        if (j < nout)
-        {
-          const bool self = (MODE == 0 && j == self_j);
+      for (int u = 0; u < U; u++)
+      {
 #pragma unroll
-          for (int w = 0; w < W; w++)
-            acc[j] += multi_term<MODE>(MODE != 1 ? sh[u][w] : 0.0, self ? sh[u][w] : a[u][j][w],
-                                       MODE != 0 ? b[u][j][w] : 0.0);
-        }
+        for (int jj = 0; jj < NB; jj++)
+          if (j0 + jj < nout)
+          {
+            const bool self = (MODE == 0 && j0 + jj == self_j);
+#pragma unroll
+            for (int w = 0; w < W; w++)
+              acc[j0 + jj] += multi_term<MODE>(MODE != 1 ? sh[u][w] : 0.0, self ? sh[u][w] : a[u][jj][w],
+                                               MODE != 0 ? b[u][jj][w] : 0.0);
+          }
+      }
     }
   }
 
@@ -588,7 +680,7 @@ __global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__
       const double sh = (MODE != 1) ? m.shared[i] : 0.0;
 #pragma unroll
       for (int j = 0; j < NO; j++)
-        if (j < nout) acc[j] += multi_term<MODE>(sh, m.A[j][i], MODE != 0 ? m.B[j][i] : 0.0);
+        if (j < nout) acc[j] += multi_term<MODE>(sh, m.A[j][i], MODE != 0 ? m.B[j % kMaxPair][i] : 0.0);
     }
   }
 
@@ -630,17 +722,18 @@ __global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__
   if (threadIdx.x == 0) s_last = take_ticket(counter);
   __syncthreads();
   if (!s_last) return;
-  /* last CTA: warp j folds output j's partials (lane-strided, then the shuffle tree) -- all outputs
-     at once instead of one block-wide pass per output; fixed order, so run-to-run identical */
+  /* last CTA: warp w folds the partials of outputs w, w + 8, .. (lane-strided, then the shuffle
+     tree) -- all outputs at once instead of one block-wide pass per output; fixed order, so
+     run-to-run identical */
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp < nout)
+    for (int j = warp; j < nout; j += kBlock / 32)
     {
-      const double* row = partials + (size_t)warp * kMaxPartialBlocks;
+      const double* row = partials + (size_t)j * kMaxPartialBlocks;
       double a          = 0.0;
       for (unsigned int i = lane; i < gridDim.x; i += 32) a += __ldcg(row + i);
       a = warp_combine<CombSum>(a);
-      if (lane == 0) s_fin[warp] = a;
+      if (lane == 0) s_fin[j] = a;
     }
   }
   if (threadIdx.x == 0) *counter = 0u;
@@ -660,7 +753,8 @@ __global__ void __launch_bounds__(kBlock)
   for (int i = threadIdx.x; i < n; i += kBlock)
   {
     const double sh = (MODE != 1) ? m.shared[i] : 0.0;
-    for (int j = 0; j < nout; j++) buf[j * n + i] = multi_term<MODE>(sh, m.A[j][i], MODE != 0 ? m.B[j][i] : 0.0);
+    for (int j = 0; j < nout; j++)
+      buf[j * n + i] = multi_term<MODE>(sh, m.A[j][i], MODE != 0 ? m.B[j % kMaxPair][i] : 0.0);
   }
   __syncthreads();
   if (threadIdx.x < nout)
@@ -724,11 +818,11 @@ static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs
   for (int j = 0; j < m.nout; j++)
   {
     wmax = min(wmax, align_width(m.A[j]));
-    wmax = min(wmax, align_width(m.B[j]));
+    if (MODE != 0) wmax = min(wmax, align_width(m.B[j]));
   }
   int W = wmax;
   if (ctx->tune.vec_width > 0 && ctx->tune.vec_width < W) W = (int)ctx->tune.vec_width;
-  const int bucket = (m.nout <= 2) ? 2 : (m.nout <= 4) ? 4 : 8;
+  const int bucket = (m.nout <= 2) ? 2 : (m.nout <= 4) ? 4 : (m.nout <= 8) ? 8 : (m.nout <= 16) ? 16 : 24;
 #define B200_MULTI_CASE(WW, NN, UU)                                                                        \
   if (W == WW && bucket == NN)                                                                             \
   return launch_multi_cfg<WW, MODE, NN, UU>(ctx, name, m, n, out, xa)
@@ -741,17 +835,31 @@ static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs
   B200_MULTI_CASE(1, 2, 2);
   B200_MULTI_CASE(1, 4, 1);
   B200_MULTI_CASE(1, 8, 1);
+  if constexpr (MODE == 0)
+  {
+    B200_MULTI_CASE(4, 16, 1);
+    B200_MULTI_CASE(4, 24, 1);
+    B200_MULTI_CASE(2, 16, 1);
+    B200_MULTI_CASE(2, 24, 1);
+    B200_MULTI_CASE(1, 16, 1);
+    B200_MULTI_CASE(1, 24, 1);
+  }
 #undef B200_MULTI_CASE
   return set_error(B200VEC_ERR_ARG, "%s: no kernel for width %d", name, W);
 }
 
-/* nout outputs in groups of <= kMaxOut (<= fewer on the exact path so the
-   staged terms fit shared memory); results land in slots [0, nout) */
+/* nout outputs in groups of <= kMaxOut / kMaxPair (fewer on the exact path so the
+   staged terms fit shared memory); every group's results land in slots [j0, j0 + group) and the
+   host collects all of them after the last launch */
 template <int MODE>
 static int launch_multi(b200vec_ctx ctx, const char* name, int nout, const double* shared, const double* const* A,
                         const double* const* B, int64_t n, double* result_host)
 {
-  if (nout > kMaxRows) return set_error(B200VEC_ERR_ARG, "%s: at most %d outputs per call", name, kMaxRows);
+  if (nout > kMaxRows)
+  {
+    ctx->scope_global = false;
+    return set_error(B200VEC_ERR_ARG, "%s: at most %d outputs per call", name, kMaxRows);
+  }
   DeviceGuard g(ctx->device);
   XArgs xa;
   const int scope = take_scope(ctx, &xa);
@@ -766,7 +874,7 @@ static int launch_multi(b200vec_ctx ctx, const char* name, int nout, const doubl
       for (int j = 0; j < nout; j++) result_host[j] = 0.0;
     return rc;
   }
-  int group = kMaxOut;
+  int group = (MODE == 0) ? kMaxOut : kMaxPair;
   if (n > 0 && n <= ctx->tune.exact_threshold)
   {
     int fit = (int)(kExactMaxElems / n);
@@ -783,24 +891,147 @@ static int launch_multi(b200vec_ctx ctx, const char* name, int nout, const doubl
     for (int j = 0; j < kMaxOut; j++)
     {
       m.A[j] = (j < m.nout) ? A[j0 + j] : nullptr;
-      m.B[j] = (j < m.nout && B) ? B[j0 + j] : nullptr;
+      if (j < kMaxPair) m.B[j] = (j < m.nout && B) ? B[j0 + j] : nullptr;
       if (MODE == 0 && m.self_j < 0 && j < m.nout && shared && m.A[j] == shared) m.self_j = j;
     }
     if (j0 > 0 && scope == 1) next_xargs(ctx, &xa); /* every group is its own collective */
     int rc = launch_multi_group<MODE>(ctx, name, m, n, j0, to_host, xa);
     if (rc) return rc;
+    /* each launch publishes under its own tag: collect this group's slots before the next launch
+       re-tags (the host would otherwise see stale tags on the earlier slots) */
+    if (to_host)
+    {
+      rc = finish_host(ctx, j0, m.nout, result_host + j0);
+      if (rc) return rc;
+    }
   }
   if (scope == 2) return finish_global_nccl(ctx, nout, B200VEC_SUM, result_host);
-  return finish_reduction(ctx, nout, result_host);
+  return B200VEC_OK;
+}
+
+/* ------------------------------------------------- fused linear combination + squared norm
+ * z = sum_i c_i X_i (z may alias X[0]) and, in the same pass, sum_k z_k^2 of the values just
+ * written.  This is the second half of a classical Gram-Schmidt step (sundials_iterative.c:137-152:
+ * N_VLinearCombination followed by N_VDotProd(v[k], v[k])) in ONE kernel and ONE host round trip:
+ * v[k] is not read back (8 B/elt saved) and the third launch + sync disappears.  The combination is
+ * k_lincomb_rows' arithmetic (register accumulator in serial's term order: bit-identical z); the
+ * norm uses the single-output reductions' epilogue (tagged partials, CTA 0 folds in fixed order).
+ * Bytes per element: 8 (nterms + 1). */
+constexpr int kLcnMaxTerms = 32;
+constexpr int kLcnBatch    = 4;
+
+struct LcNormArgs
+{
+  const double* X[kLcnMaxTerms];
+  double c[kLcnMaxTerms];
+  double* z;
+  int nterms;
+};
+
+template <int W>
+__global__ void __launch_bounds__(kBlock)
+  k_lincomb_sqnorm(const __grid_constant__ LcNormArgs a, int64_t n, unsigned long long* tagged, ResOut o, XArgs x)
+{
+  __shared__ double s_c[kLcnMaxTerms];
+  __shared__ const double* s_x[kLcnMaxTerms];
+  __shared__ double smem[kBlock / 32];
+  const int nterms = a.nterms;
+  if (threadIdx.x < nterms)
+  {
+    s_c[threadIdx.x] = a.c[threadIdx.x];
+    s_x[threadIdx.x] = a.X[threadIdx.x];
+  }
+  pdl_prologue();
+  if (x.prof && threadIdx.x == 0) atomicMin(x.prof + 6, global_ns());
+  __syncthreads();
+  double* z = a.z;
+
+  constexpr int64_t TILE = (int64_t)kBlock * W;
+  const int64_t nfull    = n / TILE;
+  double sq[W];
+#pragma unroll
+  for (int w = 0; w < W; w++) sq[w] = 0.0;
+  for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
+  {
+    const int64_t base = t * TILE + (int64_t)threadIdx.x * W;
+    double acc[W];
+    for (int i0 = 0; i0 < nterms; i0 += kLcnBatch)
+    {
+      double v[kLcnBatch][W];
+#pragma unroll
+      for (int k = 0; k < kLcnBatch; k++)
+        if (i0 + k < nterms) ldg<W>(s_x[i0 + k] + base, v[k]);
+#pragma unroll
+      for (int k = 0; k < kLcnBatch; k++)
+        if (i0 + k < nterms)
+        {
+          const double ck = s_c[i0 + k];
+#pragma unroll
+          for (int w = 0; w < W; w++)
+          {
+            const double pr = ck * v[k][w];
+            acc[w]          = (i0 + k == 0) ? pr : acc[w] + pr;
+          }
+        }
+    }
+    stg<W>(z + base, acc);
+#pragma unroll
+    for (int w = 0; w < W; w++) sq[w] += acc[w] * acc[w];
+  }
+  const int64_t tail0 = nfull * TILE;
+  if (tail0 < n && blockIdx.x == (unsigned)(nfull % gridDim.x))
+  {
+    for (int64_t i = tail0 + threadIdx.x; i < n; i += kBlock)
+    {
+      double acc = s_c[0] * s_x[0][i];
+      for (int k = 1; k < nterms; k++) acc += s_c[k] * s_x[k][i];
+      z[i] = acc;
+      sq[0] += acc * acc;
+    }
+  }
+  double v = sq[0];
+#pragma unroll
+  for (int w = 1; w < W; w++) v += sq[w];
+  v = block_combine<CombSum, kBlock>(v, smem);
+  finish_block<CombSum, kBlock, false>(v, tagged, o, x, smem, nullptr);
+}
+
+/* exact-order form (n <= exact_threshold): z as above, then thread 0 adds z_0^2, z_1^2, ...
+   strictly left to right -- the bits of serial's N_VLinearCombination + N_VDotProd */
+__global__ void __launch_bounds__(kBlock) k_lincomb_sqnorm_exact(const __grid_constant__ LcNormArgs a, int n, ResOut o, XArgs x)
+{
+  __shared__ double buf[kExactMaxElems];
+  pdl_prologue();
+  for (int i = threadIdx.x; i < n; i += kBlock)
+  {
+    double acc = a.c[0] * a.X[0][i];
+    for (int k = 1; k < a.nterms; k++) acc += a.c[k] * a.X[k][i];
+    a.z[i] = acc;
+    buf[i] = acc * acc;
+  }
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0)
+  {
+#pragma unroll 8
+    for (int i = 0; i < n; i++) s += buf[i];
+  }
+  combine_and_publish<CombSum>(s, o, x);
 }
 
 } // namespace b200
 
 using namespace b200;
 
+/* an argument error must not leave the one-shot global scope armed for the next (local) reduction */
 #define B200_RARGS(cond)                                                               \
   B200_CHECK_CTX(ctx);                                                                 \
-  if (n < 0 || (n > 0 && !(cond))) return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__)
+  if (n < 0 || (n > 0 && !(cond)))                                                     \
+  {                                                                                    \
+    ctx->scope_global = false;                                                         \
+    return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__);                   \
+  }                                                                                    \
+  (void)0
 
 extern "C" {
 
@@ -865,7 +1096,11 @@ int b200vec_dot_prod_multi(b200vec_ctx ctx, int nvec, const double* x, const dou
                            double* result_host)
 {
   B200_CHECK_CTX(ctx);
-  if (nvec < 1 || n < 0 || !Y || (n > 0 && !x)) return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__);
+  if (nvec < 1 || n < 0 || !Y || (n > 0 && !x))
+  {
+    ctx->scope_global = false;
+    return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__);
+  }
   /* nvec == 1 is N_VDotProd in the reference (serial:1007-1012): same kernel family */
   if (nvec == 1) return b200vec_dot_prod(ctx, x, Y[0], n, result_host);
   return launch_multi<0>(ctx, "dot_prod_multi", nvec, x, Y, nullptr, n, result_host);
@@ -875,12 +1110,86 @@ int b200vec_wsqr_sum_vector_array(b200vec_ctx ctx, int nvec, const double* const
                                   const double* id, int64_t n, double* result_host)
 {
   B200_CHECK_CTX(ctx);
-  if (nvec < 1 || n < 0 || !X || !W) return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__);
+  if (nvec < 1 || n < 0 || !X || !W)
+  {
+    ctx->scope_global = false;
+    return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__);
+  }
   if (nvec == 1)
     return id ? b200vec_wsqr_sum_mask(ctx, X[0], W[0], id, n, result_host)
               : b200vec_wsqr_sum(ctx, X[0], W[0], n, result_host);
   if (id) return launch_multi<2>(ctx, "wsqr_sum_mask_vector_array", nvec, id, X, W, n, result_host);
   return launch_multi<1>(ctx, "wsqr_sum_vector_array", nvec, nullptr, X, W, n, result_host);
+}
+
+/* z = sum c_j X_j and result = sum z^2 in one pass (see k_lincomb_sqnorm).  Falls back to the two
+   separate operations where the reference's N_VLinearCombination would pick a special algebraic
+   form (nvec == 1, and the +-1 / a == +-b forms of N_VLinearSum for nvec == 2 other than the
+   in-place axpy), so z is always bit-identical to serial:871-942. */
+int b200vec_linear_combination_sqnorm(b200vec_ctx ctx, int nvec, const double* c, const double* const* X, double* z,
+                                      int64_t n, double* result_host)
+{
+  B200_CHECK_CTX(ctx);
+  if (nvec < 1 || n < 0 || !c || !X || (n > 0 && !z))
+  {
+    ctx->scope_global = false;
+    return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__);
+  }
+  bool fused = nvec >= 3 && nvec <= kLcnMaxTerms;
+  if (nvec == 2)
+  {
+    const double a = c[0], b = c[1];
+    const bool axpy    = (a == 1.0 && X[0] == z);                      /* (b*x1) + z == (1*z) + b*x1 */
+    const bool special = (a == 1.0 || a == -1.0 || b == 1.0 || b == -1.0 || a == b || a == -b);
+    fused              = axpy ? (b != 1.0 && b != -1.0) : !special;
+  }
+  if (!fused)
+  {
+    const bool global = ctx->scope_global; /* the scope belongs to the reduction, not to the streaming op */
+    ctx->scope_global = false;
+    int rc            = b200vec_linear_combination(ctx, nvec, c, X, z, n);
+    if (rc) return rc;
+    ctx->scope_global = global;
+    return b200vec_dot_prod(ctx, z, z, n, result_host);
+  }
+  DeviceGuard g(ctx->device);
+  XArgs xa;
+  const int scope = take_scope(ctx, &xa);
+  if (n == 0 && scope == 0)
+  {
+    if (result_host) *result_host = 0.0;
+    return B200VEC_OK;
+  }
+  LcNormArgs a;
+  int wmax = align_width(z);
+  for (int i = 0; i < nvec; i++)
+  {
+    a.X[i] = X[i];
+    a.c[i] = c[i];
+    wmax   = min(wmax, align_width(X[i]));
+  }
+  a.z      = z;
+  a.nterms = nvec;
+  const bool to_host = (result_host != nullptr) && scope != 2;
+  const ResOut out   = next_out(ctx, 0, to_host);
+  if (n <= ctx->tune.exact_threshold) launch_k(ctx, k_lincomb_sqnorm_exact, dim3(1), dim3(kBlock), a, (int)n, out, xa);
+  else
+  {
+    int W = wmax;
+    if (ctx->tune.vec_width > 0 && ctx->tune.vec_width < W) W = (int)ctx->tune.vec_width;
+    int64_t tiles = n / ((int64_t)kBlock * W);
+    if (tiles < 1) tiles = 1;
+    int64_t cap = (int64_t)kSMs * 4; /* 4 CTAs of 256 threads per SM (60 registers): one resident wave */
+    if (ctx->tune.max_blocks != kMaxBlocksDef && cap > ctx->tune.max_blocks) cap = ctx->tune.max_blocks;
+    const int grid = (int)((tiles < cap) ? tiles : cap);
+    if (W == 4) launch_k(ctx, k_lincomb_sqnorm<4>, dim3(grid), dim3(kBlock), a, n, ctx->d_tagged, out, xa);
+    else if (W == 2) launch_k(ctx, k_lincomb_sqnorm<2>, dim3(grid), dim3(kBlock), a, n, ctx->d_tagged, out, xa);
+    else launch_k(ctx, k_lincomb_sqnorm<1>, dim3(grid), dim3(kBlock), a, n, ctx->d_tagged, out, xa);
+  }
+  int rc = check_launch(ctx, "linear_combination_sqnorm");
+  if (rc) return rc;
+  if (scope == 2) return finish_global_nccl(ctx, 1, B200VEC_SUM, result_host);
+  return finish_host(ctx, 0, 1, result_host);
 }
 
 } /* extern "C" */

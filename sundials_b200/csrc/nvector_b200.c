@@ -18,6 +18,8 @@
  */
 #include "nvector_b200.h"
 
+#include <sundials/priv/sundials_context_impl.h>
+
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
@@ -34,17 +36,29 @@
 /* ----------------------------------------------------------------------
  * failure handling
  * -------------------------------------------------------------------- */
-static void b200_fatal(const char* where, int rc)
+/* A failed kernel launch / CUDA call inside a void or scalar op has no return channel
+   (sundials_nvector.h).  It is (1) reported on stderr, (2) recorded in the vector's SUNContext
+   (sunctx->last_err = SUN_ERR_EXT_FAIL, what SUNCheckLastErr() inspects), and scalar ops return
+   NaN so that the calling integrator fails through its own error path (a NaN norm fails every
+   error test).  Set B200VEC_ABORT_ON_ERROR=1 to stop the process at the first failure instead. */
+static void b200_fail(N_Vector v, const char* where, int rc)
 {
-  fprintf(stderr, "[nvector_b200] FATAL in %s: error %d: %s\n", where, rc, b200vec_last_error());
-  fflush(stderr);
-  abort();
+  static int reported = 0;
+  if (reported < 8)
+  {
+    reported++;
+    fprintf(stderr, "[nvector_b200] ERROR in %s: error %d: %s\n", where, rc, b200vec_last_error());
+    fflush(stderr);
+  }
+  if (v && v->sunctx) v->sunctx->last_err = SUN_ERR_EXT_FAIL;
+  const char* e = getenv("B200VEC_ABORT_ON_ERROR");
+  if (e && e[0] && e[0] != '0') abort();
 }
 
-#define CHECK_VOID(call)                       \
-  do {                                         \
-    int rc_ = (call);                          \
-    if (rc_ != B200VEC_OK) b200_fatal(__func__, rc_); \
+#define CHECK_ON(v, call)                                \
+  do {                                                   \
+    int rc_ = (call);                                    \
+    if (rc_ != B200VEC_OK) b200_fail((v), __func__, rc_); \
   } while (0)
 
 static SUNErrCode map_err(int rc)
@@ -62,7 +76,7 @@ static SUNErrCode map_err(int rc)
    after any op returns, so streaming ops end with a stream sync */
 static void coherent_sync(N_Vector v)
 {
-  if (NVC(v)->mem_kind != B200_MEM_DEVICE) CHECK_VOID(b200vec_ctx_sync(NCTX(v)));
+  if (NVC(v)->mem_kind != B200_MEM_DEVICE) CHECK_ON(v, b200vec_ctx_sync(NCTX(v)));
 }
 
 /* SUNRsqrt (include/sundials/sundials_math.h:83) */
@@ -331,14 +345,14 @@ sunrealtype* N_VGetHostArrayPointer_B200(N_Vector v)
     if (!c->host_data && c->length > 0)
     { /* lazily created pinned mirror (the reference allocates it eagerly, cuda:2226) */
       void* p = NULL;
-      CHECK_VOID(b200vec_malloc_host(c->ctx, (size_t)c->length * sizeof(sunrealtype), &p));
+      CHECK_ON(v, b200vec_malloc_host(c->ctx, (size_t)c->length * sizeof(sunrealtype), &p));
       c->host_data = (sunrealtype*)p;
       c->own_host  = SUNTRUE;
     }
     return c->host_data;
   }
   /* host-coherent kinds: make pending kernels visible before the host looks */
-  CHECK_VOID(b200vec_ctx_sync(c->ctx));
+  CHECK_ON(v, b200vec_ctx_sync(c->ctx));
   return c->host_data;
 }
 
@@ -383,7 +397,7 @@ void N_VCopyToDevice_B200(N_Vector v)
 {
   N_VectorContent_B200 c = NVC(v);
   if (c->mem_kind != B200_MEM_DEVICE || !c->host_data) return;
-  CHECK_VOID(b200vec_copy_h2d(c->ctx, c->device_data, c->host_data, (size_t)c->length * sizeof(sunrealtype), 1));
+  CHECK_ON(v, b200vec_copy_h2d(c->ctx, c->device_data, c->host_data, (size_t)c->length * sizeof(sunrealtype), 1));
 }
 
 void N_VCopyFromDevice_B200(N_Vector v)
@@ -391,12 +405,24 @@ void N_VCopyFromDevice_B200(N_Vector v)
   N_VectorContent_B200 c = NVC(v);
   if (c->mem_kind != B200_MEM_DEVICE)
   {
-    CHECK_VOID(b200vec_ctx_sync(c->ctx));
+    CHECK_ON(v, b200vec_ctx_sync(c->ctx));
     return;
   }
   (void)N_VGetHostArrayPointer_B200(v);
-  CHECK_VOID(b200vec_copy_d2h(c->ctx, c->host_data, c->device_data, (size_t)c->length * sizeof(sunrealtype), 1));
+  CHECK_ON(v, b200vec_copy_d2h(c->ctx, c->host_data, c->device_data, (size_t)c->length * sizeof(sunrealtype), 1));
 }
+
+/* asynchronous upload on the context's copy stream: ordered after the vector work issued so far,
+   overlapping whatever is issued next; N_VCopyJoin_B200 makes the context's stream wait for it
+   (no host blocking).  The reference has only the synchronous form (cuda:553). */
+void N_VCopyToDeviceAsync_B200(N_Vector v)
+{
+  N_VectorContent_B200 c = NVC(v);
+  if (c->mem_kind != B200_MEM_DEVICE || !c->host_data) return;
+  CHECK_ON(v, b200vec_copy_h2d_async(c->ctx, c->device_data, c->host_data, (size_t)c->length * sizeof(sunrealtype)));
+}
+
+void N_VCopyJoin_B200(N_Vector v) { CHECK_ON(v, b200vec_copy_join(NCTX(v))); }
 
 SUNErrCode N_VSetStream_B200(N_Vector v, void* stream) { return map_err(b200vec_ctx_set_stream(NCTX(v), stream)); }
 
@@ -476,55 +502,55 @@ void N_VDestroy_B200(N_Vector v)
  * -------------------------------------------------------------------- */
 void N_VLinearSum_B200(sunrealtype a, N_Vector x, sunrealtype b, N_Vector y, N_Vector z)
 {
-  CHECK_VOID(b200vec_linear_sum(NCTX(z), a, NDEV(x), b, NDEV(y), NDEV(z), NLEN(z)));
+  CHECK_ON(z, b200vec_linear_sum(NCTX(z), a, NDEV(x), b, NDEV(y), NDEV(z), NLEN(z)));
   coherent_sync(z);
 }
 
 void N_VConst_B200(sunrealtype c, N_Vector z)
 {
-  CHECK_VOID(b200vec_const(NCTX(z), c, NDEV(z), NLEN(z)));
+  CHECK_ON(z, b200vec_const(NCTX(z), c, NDEV(z), NLEN(z)));
   coherent_sync(z);
 }
 
 void N_VProd_B200(N_Vector x, N_Vector y, N_Vector z)
 {
-  CHECK_VOID(b200vec_prod(NCTX(z), NDEV(x), NDEV(y), NDEV(z), NLEN(z)));
+  CHECK_ON(z, b200vec_prod(NCTX(z), NDEV(x), NDEV(y), NDEV(z), NLEN(z)));
   coherent_sync(z);
 }
 
 void N_VDiv_B200(N_Vector x, N_Vector y, N_Vector z)
 {
-  CHECK_VOID(b200vec_div(NCTX(z), NDEV(x), NDEV(y), NDEV(z), NLEN(z)));
+  CHECK_ON(z, b200vec_div(NCTX(z), NDEV(x), NDEV(y), NDEV(z), NLEN(z)));
   coherent_sync(z);
 }
 
 void N_VScale_B200(sunrealtype c, N_Vector x, N_Vector z)
 {
-  CHECK_VOID(b200vec_scale(NCTX(z), c, NDEV(x), NDEV(z), NLEN(z)));
+  CHECK_ON(z, b200vec_scale(NCTX(z), c, NDEV(x), NDEV(z), NLEN(z)));
   coherent_sync(z);
 }
 
 void N_VAbs_B200(N_Vector x, N_Vector z)
 {
-  CHECK_VOID(b200vec_abs(NCTX(z), NDEV(x), NDEV(z), NLEN(z)));
+  CHECK_ON(z, b200vec_abs(NCTX(z), NDEV(x), NDEV(z), NLEN(z)));
   coherent_sync(z);
 }
 
 void N_VInv_B200(N_Vector x, N_Vector z)
 {
-  CHECK_VOID(b200vec_inv(NCTX(z), NDEV(x), NDEV(z), NLEN(z)));
+  CHECK_ON(z, b200vec_inv(NCTX(z), NDEV(x), NDEV(z), NLEN(z)));
   coherent_sync(z);
 }
 
 void N_VAddConst_B200(N_Vector x, sunrealtype b, N_Vector z)
 {
-  CHECK_VOID(b200vec_add_const(NCTX(z), NDEV(x), b, NDEV(z), NLEN(z)));
+  CHECK_ON(z, b200vec_add_const(NCTX(z), NDEV(x), b, NDEV(z), NLEN(z)));
   coherent_sync(z);
 }
 
 void N_VCompare_B200(sunrealtype c, N_Vector x, N_Vector z)
 {
-  CHECK_VOID(b200vec_compare(NCTX(z), c, NDEV(x), NDEV(z), NLEN(z)));
+  CHECK_ON(z, b200vec_compare(NCTX(z), c, NDEV(x), NDEV(z), NLEN(z)));
   coherent_sync(z);
 }
 
@@ -537,88 +563,88 @@ void N_VCompare_B200(sunrealtype c, N_Vector x, N_Vector z)
  * SUM / MAX / MIN implied by the op.
  * -------------------------------------------------------------------- */
 #define GLOBAL_SCOPE(v) \
-  do { if (NDIST(v)) CHECK_VOID(b200vec_ctx_set_scope(NCTX(v), B200VEC_SCOPE_GLOBAL)); } while (0)
+  do { if (NDIST(v)) CHECK_ON(v, b200vec_ctx_set_scope(NCTX(v), B200VEC_SCOPE_GLOBAL)); } while (0)
 
 sunrealtype N_VDotProdLocal_B200(N_Vector x, N_Vector y)
 {
-  double r;
-  CHECK_VOID(b200vec_dot_prod(NCTX(x), NDEV(x), NDEV(y), NLEN(x), &r));
+  double r = NAN;
+  CHECK_ON(x, b200vec_dot_prod(NCTX(x), NDEV(x), NDEV(y), NLEN(x), &r));
   return r;
 }
 
 sunrealtype N_VDotProd_B200(N_Vector x, N_Vector y)
 {
-  double r;
+  double r = NAN;
   GLOBAL_SCOPE(x); /* nvector_manyvector.c:815 */
-  CHECK_VOID(b200vec_dot_prod(NCTX(x), NDEV(x), NDEV(y), NLEN(x), &r));
+  CHECK_ON(x, b200vec_dot_prod(NCTX(x), NDEV(x), NDEV(y), NLEN(x), &r));
   return r;
 }
 
 sunrealtype N_VMaxNormLocal_B200(N_Vector x)
 {
-  double r;
-  CHECK_VOID(b200vec_max_norm(NCTX(x), NDEV(x), NLEN(x), &r));
+  double r = NAN;
+  CHECK_ON(x, b200vec_max_norm(NCTX(x), NDEV(x), NLEN(x), &r));
   return r;
 }
 
 sunrealtype N_VMaxNorm_B200(N_Vector x)
 {
-  double r;
+  double r = NAN;
   GLOBAL_SCOPE(x); /* :869 */
-  CHECK_VOID(b200vec_max_norm(NCTX(x), NDEV(x), NLEN(x), &r));
+  CHECK_ON(x, b200vec_max_norm(NCTX(x), NDEV(x), NLEN(x), &r));
   return r;
 }
 
 sunrealtype N_VMinLocal_B200(N_Vector x)
 {
-  double r;
-  CHECK_VOID(b200vec_min(NCTX(x), NDEV(x), NLEN(x), &r));
+  double r = NAN;
+  CHECK_ON(x, b200vec_min(NCTX(x), NDEV(x), NLEN(x), &r));
   return r;
 }
 
 sunrealtype N_VMin_B200(N_Vector x)
 {
-  double r;
+  double r = NAN;
   GLOBAL_SCOPE(x); /* :1107 */
-  CHECK_VOID(b200vec_min(NCTX(x), NDEV(x), NLEN(x), &r));
+  CHECK_ON(x, b200vec_min(NCTX(x), NDEV(x), NLEN(x), &r));
   return r;
 }
 
 sunrealtype N_VL1NormLocal_B200(N_Vector x)
 {
-  double r;
-  CHECK_VOID(b200vec_l1_norm(NCTX(x), NDEV(x), NLEN(x), &r));
+  double r = NAN;
+  CHECK_ON(x, b200vec_l1_norm(NCTX(x), NDEV(x), NLEN(x), &r));
   return r;
 }
 
 sunrealtype N_VL1Norm_B200(N_Vector x)
 {
-  double r;
+  double r = NAN;
   GLOBAL_SCOPE(x); /* :1203 */
-  CHECK_VOID(b200vec_l1_norm(NCTX(x), NDEV(x), NLEN(x), &r));
+  CHECK_ON(x, b200vec_l1_norm(NCTX(x), NDEV(x), NLEN(x), &r));
   return r;
 }
 
 sunrealtype N_VWSqrSumLocal_B200(N_Vector x, N_Vector w)
 {
-  double r;
-  CHECK_VOID(b200vec_wsqr_sum(NCTX(x), NDEV(x), NDEV(w), NLEN(x), &r));
+  double r = NAN;
+  CHECK_ON(x, b200vec_wsqr_sum(NCTX(x), NDEV(x), NDEV(w), NLEN(x), &r));
   return r;
 }
 
 sunrealtype N_VWSqrSumMaskLocal_B200(N_Vector x, N_Vector w, N_Vector id)
 {
-  double r;
-  CHECK_VOID(b200vec_wsqr_sum_mask(NCTX(x), NDEV(x), NDEV(w), NDEV(id), NLEN(x), &r));
+  double r = NAN;
+  CHECK_ON(x, b200vec_wsqr_sum_mask(NCTX(x), NDEV(x), NDEV(w), NDEV(id), NLEN(x), &r));
   return r;
 }
 
 static sunrealtype wsqr_global(N_Vector x, N_Vector w, N_Vector id)
 {
-  double r;
+  double r = NAN;
   GLOBAL_SCOPE(x); /* :956, :1050, :1128 */
-  if (id) CHECK_VOID(b200vec_wsqr_sum_mask(NCTX(x), NDEV(x), NDEV(w), NDEV(id), NLEN(x), &r));
-  else CHECK_VOID(b200vec_wsqr_sum(NCTX(x), NDEV(x), NDEV(w), NLEN(x), &r));
+  if (id) CHECK_ON(x, b200vec_wsqr_sum_mask(NCTX(x), NDEV(x), NDEV(w), NDEV(id), NLEN(x), &r));
+  else CHECK_ON(x, b200vec_wsqr_sum(NCTX(x), NDEV(x), NDEV(w), NLEN(x), &r));
   return r;
 }
 
@@ -637,46 +663,50 @@ sunrealtype N_VWL2Norm_B200(N_Vector x, N_Vector w) { return rsqrt_guard(wsqr_gl
 
 sunbooleantype N_VInvTestLocal_B200(N_Vector x, N_Vector z)
 {
-  double r;
-  CHECK_VOID(b200vec_inv_test(NCTX(z), NDEV(x), NDEV(z), NLEN(z), &r));
+  double r = NAN;
+  CHECK_ON(z, b200vec_inv_test(NCTX(z), NDEV(x), NDEV(z), NLEN(z), &r));
+  coherent_sync(z); /* the scalar arrives before the kernel has drained: host-coherent z needs the sync */
   return (r > 0.5) ? SUNTRUE : SUNFALSE;
 }
 
 sunbooleantype N_VInvTest_B200(N_Vector x, N_Vector z)
 {
-  double r;
-  GLOBAL_SCOPE(x); /* :1277 */
-  CHECK_VOID(b200vec_inv_test(NCTX(z), NDEV(x), NDEV(z), NLEN(z), &r));
+  double r = NAN;
+  GLOBAL_SCOPE(z); /* :1277 -- on the context that launches */
+  CHECK_ON(z, b200vec_inv_test(NCTX(z), NDEV(x), NDEV(z), NLEN(z), &r));
+  coherent_sync(z);
   return (r > 0.5) ? SUNTRUE : SUNFALSE;
 }
 
 sunbooleantype N_VConstrMaskLocal_B200(N_Vector c, N_Vector x, N_Vector m)
 {
-  double r;
-  CHECK_VOID(b200vec_constr_mask(NCTX(m), NDEV(c), NDEV(x), NDEV(m), NLEN(m), &r));
+  double r = NAN;
+  CHECK_ON(m, b200vec_constr_mask(NCTX(m), NDEV(c), NDEV(x), NDEV(m), NLEN(m), &r));
+  coherent_sync(m);
   return (r > 0.5) ? SUNTRUE : SUNFALSE;
 }
 
 sunbooleantype N_VConstrMask_B200(N_Vector c, N_Vector x, N_Vector m)
 {
-  double r;
-  GLOBAL_SCOPE(x); /* :1339 */
-  CHECK_VOID(b200vec_constr_mask(NCTX(m), NDEV(c), NDEV(x), NDEV(m), NLEN(m), &r));
+  double r = NAN;
+  GLOBAL_SCOPE(m); /* :1339 -- on the context that launches */
+  CHECK_ON(m, b200vec_constr_mask(NCTX(m), NDEV(c), NDEV(x), NDEV(m), NLEN(m), &r));
+  coherent_sync(m);
   return (r > 0.5) ? SUNTRUE : SUNFALSE;
 }
 
 sunrealtype N_VMinQuotientLocal_B200(N_Vector num, N_Vector denom)
 {
-  double r;
-  CHECK_VOID(b200vec_min_quotient(NCTX(num), NDEV(num), NDEV(denom), NLEN(num), &r));
+  double r = NAN;
+  CHECK_ON(num, b200vec_min_quotient(NCTX(num), NDEV(num), NDEV(denom), NLEN(num), &r));
   return r;
 }
 
 sunrealtype N_VMinQuotient_B200(N_Vector num, N_Vector denom)
 {
-  double r;
+  double r = NAN;
   GLOBAL_SCOPE(num); /* :1399 */
-  CHECK_VOID(b200vec_min_quotient(NCTX(num), NDEV(num), NDEV(denom), NLEN(num), &r));
+  CHECK_ON(num, b200vec_min_quotient(NCTX(num), NDEV(num), NDEV(denom), NLEN(num), &r));
   return r;
 }
 
@@ -725,6 +755,20 @@ SUNErrCode N_VLinearCombination_B200(int nvec, sunrealtype* c, N_Vector* X, N_Ve
   /* nvec <= 2 delegate to Scale / LinearSum whose in-place forms are chosen on
      HANDLE identity (serial:885-898); data-pointer identity is equivalent here */
   int rc = b200vec_linear_combination(NCTX(z), nvec, c, tx.p, NDEV(z), NLEN(z));
+  table_free(&tx);
+  if (!rc) coherent_sync(z);
+  return map_err(rc);
+}
+
+/* z = sum c_i X_i and *sqnorm = z . z (GLOBAL on a distributed vector) in one kernel and one host
+   round trip: N_VLinearCombination + N_VDotProd(z, z) of sundials_iterative.c:137-152 */
+SUNErrCode N_VLinearCombinationSqNorm_B200(int nvec, sunrealtype* c, N_Vector* X, N_Vector z, sunrealtype* sqnorm)
+{
+  if (nvec < 1 || !sqnorm) return SUN_ERR_ARG_OUTOFRANGE;
+  ptr_table tx;
+  if (gather(&tx, X, nvec)) return SUN_ERR_MALLOC_FAIL;
+  int rc = NDIST(z) ? b200vec_ctx_set_scope(NCTX(z), B200VEC_SCOPE_GLOBAL) : B200VEC_OK;
+  if (!rc) rc = b200vec_linear_combination_sqnorm(NCTX(z), nvec, c, tx.p, NDEV(z), NLEN(z), sqnorm);
   table_free(&tx);
   if (!rc) coherent_sync(z);
   return map_err(rc);

@@ -303,6 +303,20 @@ def N_VLinearCombination(c: Sequence[float], X: Sequence[NVector], z: NVector) -
           "N_VLinearCombination")
 
 
+def N_VLinearCombinationSqNorm(c: Sequence[float], X: Sequence[NVector], z: NVector) -> float:
+    """z = sum c_i X_i and return z . z, one kernel (b200vec_linear_combination_sqnorm)."""
+    lib = _L(z)
+    if z.distributed:
+        check(lib.b200vec_linear_combination_sqnorm(z.ctx.h, len(X), _coef(c), _table(X), z.ptr, len(z), None),
+              "N_VLinearCombinationSqNorm")
+        z.ctx.allreduce_slots(1, B200VEC_SUM)
+        return z.ctx.fetch(1)[0]
+    r = C.c_double()
+    check(lib.b200vec_linear_combination_sqnorm(z.ctx.h, len(X), _coef(c), _table(X), z.ptr, len(z), C.byref(r)),
+          "N_VLinearCombinationSqNorm")
+    return r.value
+
+
 def N_VScaleAddMulti(a: Sequence[float], x: NVector, Y: Sequence[NVector], Z: Sequence[NVector]) -> None:
     check(_L(x).b200vec_scale_add_multi(x.ctx.h, len(Y), _coef(a), x.ptr, _table(Y), _table(Z), len(x)),
           "N_VScaleAddMulti")

@@ -9,6 +9,8 @@
  *
  *   test_gs_b200 <n> <maxl> <tol>      tol = 0 demands bit-identical results
  *
+ * A third pass compares the reference's SUNClassicalGS on nvector_serial with the fused
+ * SUNClassicalGS_B200 (include/sundials_iterative_b200.h) on NVECTOR_B200.
  * Prints one line per (gstype, k) and exits with the number of mismatches.
  */
 #include <math.h>
@@ -21,6 +23,13 @@
 #include <sundials/sundials_math.h>
 
 #include "nvector_b200.h"
+#include "sundials_iterative_b200.h"
+
+#define FUSED_CLASSICAL_GS 3 /* serial: reference SUNClassicalGS; B200: SUNClassicalGS_B200 (2 kernels per column) */
+static const char* gsname(int t)
+{
+  return t == SUN_MODIFIED_GS ? "modified " : t == SUN_CLASSICAL_GS ? "classical" : "fused-cgs";
+}
 
 static void fill(sunrealtype* d, sunindextype n, unsigned seed)
 {
@@ -47,7 +56,7 @@ int main(int argc, char** argv)
   if (SUNContext_Create(SUN_COMM_NULL, &ctx)) return 99;
   int bad = 0;
 
-  for (int gstype = SUN_MODIFIED_GS; gstype <= SUN_CLASSICAL_GS; gstype++)
+  for (int gstype = SUN_MODIFIED_GS; gstype <= FUSED_CLASSICAL_GS; gstype++)
   {
     N_Vector ts = N_VNew_Serial(n, ctx);
     N_Vector tb = N_VNew_B200(n, ctx);
@@ -83,10 +92,15 @@ int main(int argc, char** argv)
         SUNModifiedGS(Vs, Hs, k, maxl, &nrm_s);
         SUNModifiedGS(Vb, Hb, k, maxl, &nrm_b);
       }
-      else
+      else if (gstype == SUN_CLASSICAL_GS)
       {
         SUNClassicalGS(Vs, Hs, k, maxl, &nrm_s, ss, ws);
         SUNClassicalGS(Vb, Hb, k, maxl, &nrm_b, sb, wb);
+      }
+      else
+      {
+        SUNClassicalGS(Vs, Hs, k, maxl, &nrm_s, ss, ws);
+        SUNClassicalGS_B200(Vb, Hb, k, maxl, &nrm_b, sb, wb);
       }
       int kb = differ(nrm_s, nrm_b, tol, nrm_s);
       double hmax = 0;
@@ -99,7 +113,7 @@ int main(int argc, char** argv)
       N_VScale(1.0 / nrm_s, Vs[k], Vs[k]);
       N_VScale(1.0 / nrm_b, Vb[k], Vb[k]);
       printf("%s k=%d  norm serial %.17g b200 %.17g  max|dh| %.3g  %s\n",
-             gstype == SUN_MODIFIED_GS ? "modified " : "classical", k, nrm_s, nrm_b, hmax, kb ? "MISMATCH" : "ok");
+             gsname(gstype), k, nrm_s, nrm_b, hmax, kb ? "MISMATCH" : "ok");
       bad += kb;
     }
     /* final basis */
@@ -116,7 +130,7 @@ int main(int argc, char** argv)
       }
     }
     if (tol > 0.0 && vmax > tol * 10) bad++;
-    printf("%s basis max|dv| = %.3g\n", gstype == SUN_MODIFIED_GS ? "modified " : "classical", vmax);
+    printf("%s basis max|dv| = %.3g\n", gsname(gstype), vmax);
     for (int i = 0; i <= maxl; i++)
     {
       free(Hs[i]);

@@ -195,3 +195,156 @@ def test_length_2pow30_plus_ragged_tail_int64_indexing(be):
     assert float(w.data[n - 2]) == -6.0 and float(w.data[n - 1]) == 3.0
     assert float(z.data[n - 2]) == -22.5 and float(z.data[n - 1]) == 4.5
     assert nv.N_VMin(z) == -22.5
+
+
+# ------------------------------------------------------------------ round 2
+@pytest.fixture(scope="module")
+def pbe():
+    """the SHIPPED C host layer (N_V*_B200 of nvector_b200.c) as a backend"""
+    from _plugin_backend import PluginBackend
+
+    return PluginBackend()
+
+
+@pytest.mark.parametrize("n", [5, 1000])
+def test_c_host_layer_all_ops_small_n_bit_exact(pbe, oracle, n):
+    _run_cases(all_cases(), pbe, oracle, n, 43 + n, exact=True)
+
+
+def test_c_host_layer_streaming_and_fused_bit_exact(pbe, oracle):
+    _run_cases(streaming_cases() + fused_cases() + vector_array_cases(), pbe, oracle, 4099, 47, exact=False)
+
+
+def test_c_host_layer_reductions_within_tolerance(pbe, oracle):
+    _run_cases(reduction_cases(), pbe, oracle, 300_001, 53, exact=False)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+def test_oracle_parity_at_the_benchmarked_length_2pow24(be, oracle):
+    """Random data at BASELINE's length (2^24 per vector, nv = 8): streaming / fused results
+    bit-exact against the CPU oracle, tree reductions within 1e-13 of sum|terms|."""
+    from sundials_b200 import nvector as nv
+
+    n, nvec = 1 << 24, 8
+    rng = np.random.default_rng(2024)
+    X = [rng.uniform(-1, 1, n) for _ in range(nvec)]
+    w = rng.uniform(0.5, 1.5, n)
+    idm = rng.integers(0, 2, n).astype(np.float64)
+    dX = [nv.N_VMake(torch.from_numpy(a).cuda(), be.ctx) for a in X]
+    dw, did = nv.N_VMake(torch.from_numpy(w).cuda(), be.ctx), nv.N_VMake(torch.from_numpy(idm).cuda(), be.ctx)
+    z, zo = nv.N_VNew(n, be.ctx), np.empty(n)
+    # N_VLinearSum, general form
+    nv.N_VLinearSum(0.3, dX[0], -2.1, dX[1], z)
+    oracle.linear_sum(0.3, X[0], -2.1, X[1], zo)
+    assert np.array_equal(_bits(z.data.cpu().numpy()), _bits(zo)), "N_VLinearSum"
+    # N_VLinearCombination nv = 8
+    c = [0.11 * (j + 1) * (-1) ** j for j in range(nvec)]
+    nv.N_VLinearCombination(c, dX, z)
+    oracle.linear_combination(c, X, zo)
+    assert np.array_equal(_bits(z.data.cpu().numpy()), _bits(zo)), "N_VLinearCombination"
+    # N_VScaleAddMulti nv = 4 (outputs into fresh vectors)
+    Y, Zo = X[1:5], [np.empty(n) for _ in range(4)]
+    dZ = [nv.N_VNew(n, be.ctx) for _ in range(4)]
+    nv.N_VScaleAddMulti(c[:4], dX[0], dX[1:5], dZ)
+    oracle.scale_add_multi(c[:4], X[0], Y, Zo)
+    for j in range(4):
+        assert np.array_equal(_bits(dZ[j].data.cpu().numpy()), _bits(Zo[j])), f"N_VScaleAddMulti[{j}]"
+    del dZ, Zo
+    # reductions.  At 2^24 terms nvector_serial's strictly sequential sum itself carries ~sqrt(n) eps
+    # of rounding, more than the 1e-13 bar in unlucky cases, so every sum is checked three ways
+    # against a long-double reference sum of the SAME double-precision terms:
+    #   (a) ours is accurate:      |ours - exact|   <= 4e-15 sum|terms|   (pairwise tree, log2(n) eps)
+    #   (b) the north-star bar:    |ours - serial|  <= 1e-13 sum|terms|, or, where serial's own rounding
+    #       exceeds that,          |ours - serial|  <= |serial - exact| + 4e-15 sum|terms|
+    def check_sum(name, got, want, terms):
+        exact = float(np.sum(terms.astype(np.longdouble)))
+        scale = float(np.abs(terms).sum())
+        assert abs(got - exact) <= 4e-15 * scale, (name, "accuracy", got, exact)
+        assert abs(got - want) <= max(RTOL * scale, abs(want - exact) + 4e-15 * scale), (name, got, want, exact)
+
+    check_sum("N_VDotProd", nv.N_VDotProd(dX[0], dX[1]), oracle.dot_prod(X[0], X[1]), X[0] * X[1])
+    check_sum("N_VL1Norm", nv.N_VL1Norm(dX[4]), oracle.l1_norm(X[4]), np.abs(X[4]))
+    assert nv.N_VMaxNorm(dX[2]) == oracle.max_norm(X[2]), "N_VMaxNorm"
+    assert nv.N_VMin(dX[2]) == oracle.min(X[2]), "N_VMin"
+    p = X[3] * w
+    check_sum("N_VWSqrSumMaskLocal", nv.N_VWSqrSumMaskLocal(dX[3], dw, did), oracle.wsqr_sum_mask(X[3], w, idm),
+              np.where(idm > 0, p * p, 0.0))
+    got, want = nv.N_VWrmsNormMask(dX[3], dw, did), oracle.wrms_norm_mask(X[3], w, idm)
+    assert abs(got - want) <= 2 * RTOL * want, ("N_VWrmsNormMask", got, want)
+    got, want = nv.N_VDotProdMulti(dX[0], dX), oracle.dot_prod_multi(X[0], X)
+    for j in range(nvec):
+        check_sum(f"N_VDotProdMulti[{j}]", got[j], float(want[j]), X[0] * X[j])
+    W = [w] * nvec
+    got, want = np.array(nv.N_VWrmsNormVectorArray(dX, [dw] * nvec)), oracle.wrms_norm_vector_array(X, W)
+    for j in range(nvec):  # norm = sqrt(sum / n): compare the sums
+        p = X[j] * w
+        check_sum(f"N_VWrmsNormVectorArray[{j}]", float(got[j]) ** 2 * n, float(want[j]) ** 2 * n, p * p)
+    assert np.all(np.abs(got - want) <= 2 * RTOL * want), ("N_VWrmsNormVectorArray", got, want)
+
+
+@pytest.mark.parametrize("n", [7, 1000, 1025, 300_001])
+@pytest.mark.parametrize("nvec", [2, 3, 6, 21, 32, 33])
+def test_linear_combination_sqnorm_matches_the_two_reference_ops(be, oracle, n, nvec):
+    """the fused second half of a classical Gram-Schmidt step: z bit-identical to
+    N_VLinearCombination, the norm equal to N_VDotProd(z, z) (bitwise on the exact path)"""
+    from sundials_b200 import nvector as nv
+
+    rng = np.random.default_rng(100 * nvec + n % 97)
+    X = [rng.uniform(-1, 1, n) for _ in range(nvec)]
+    for form in ("in-place c0=1", "general"):
+        c = [1.0 if form != "general" else 0.7] + [float(v) for v in rng.uniform(-0.9, 0.9, nvec - 1)]
+        Xo = [a.copy() for a in X]
+        dX = [nv.N_VMake(torch.from_numpy(a.copy()).cuda(), be.ctx) for a in X]
+        if form == "general":
+            zo, dz = np.empty(n), nv.N_VNew(n, be.ctx)
+        else:
+            zo, dz = Xo[0], dX[0]
+        got = nv.N_VLinearCombinationSqNorm(c, dX, dz)
+        oracle.linear_combination(c, Xo, zo)
+        want = oracle.dot_prod(zo, zo)
+        assert np.array_equal(_bits(dz.data.cpu().numpy()), _bits(zo)), (form, "z")
+        if n <= 1024:
+            assert got == want, (form, got, want)
+        else:
+            assert abs(got - want) <= RTOL * want, (form, got, want)
+
+
+@pytest.mark.parametrize("n", [1000, 70_001])
+@pytest.mark.parametrize("nvec", [9, 16, 21, 24, 25, 40])
+def test_wide_dot_prod_multi(be, oracle, n, nvec):
+    """more than 8 outputs: one launch up to 24 (GMRES maxl = 20 issues a 21-wide one), slices beyond;
+    x itself among the Y (classical Gram-Schmidt)"""
+    from sundials_b200 import nvector as nv
+
+    rng = np.random.default_rng(nvec * 7 + n % 13)
+    x = rng.uniform(-1, 1, n)
+    Y = [rng.uniform(-1, 1, n) for _ in range(nvec - 1)] + [x]
+    dx = nv.N_VMake(torch.from_numpy(x).cuda(), be.ctx)
+    dY = [nv.N_VMake(torch.from_numpy(a).cuda(), be.ctx) for a in Y[:-1]] + [dx]
+    be.ctx.set_tuning("count_launches", 1)
+    got = np.array(nv.N_VDotProdMulti(dx, dY))
+    launches = be.ctx.launch_count()
+    be.ctx.set_tuning("count_launches", 0)
+    want = oracle.dot_prod_multi(x, Y)
+    if n <= 1024:
+        assert np.array_equal(_bits(got), _bits(want))
+    else:
+        lim = np.array([RTOL * float(np.abs(x * y).sum()) for y in Y])
+        assert np.all(np.abs(got - want) <= lim), (got, want)
+        assert launches == (1 if nvec <= 24 else 2), launches
+
+
+def test_min_returns_a_nan_at_x0_like_serial(be, oracle):
+    """N_VMin_Serial starts from x[0]: a NaN there is returned, a NaN elsewhere never wins"""
+    from sundials_b200 import nvector as nv
+
+    for n in (10, 5000, 1 << 21):
+        x = np.linspace(1.0, 2.0, n)
+        x[n // 2] = np.nan
+        assert nv.N_VMin(nv.N_VMake(torch.from_numpy(x).cuda(), be.ctx)) == oracle.min(x) == 1.0
+        x[0] = np.nan
+        got, want = nv.N_VMin(nv.N_VMake(torch.from_numpy(x).cuda(), be.ctx)), oracle.min(x)
+        assert np.isnan(got) and np.isnan(want)

@@ -64,6 +64,54 @@ def test_gram_schmidt_tolerance_large():
     assert "SUCCESS" in r.stdout
 
 
+def test_fused_classical_gs_matches_reference_cgs_on_serial():
+    """third pass of test_gs_b200: SUNClassicalGS_B200 (2 kernels per column) on NVECTOR_B200 against the
+    reference's SUNClassicalGS on nvector_serial -- bit-identical at n = 1000, 1e-13 at 300 000"""
+    r = _run("test_gs_b200", 1000, 10, 0)
+    assert r.returncode == 0 and r.stdout.count("fused-cgs k=") == 10 and "MISMATCH" not in r.stdout, r.stdout
+    r = _run("test_gs_b200", 300_000, 20, 1e-13)
+    assert r.returncode == 0 and r.stdout.count("fused-cgs k=") == 20 and "MISMATCH" not in r.stdout, r.stdout
+
+
+def test_spgmr_uses_the_fused_gs_by_symbol_interposition():
+    """the reference's UNMODIFIED SPGMR unit test (classical Gram-Schmidt, gstype 2) with
+    libsundials_b200gs.so preloaded: its SUNClassicalGS calls land in SUNClassicalGS_B200
+    (interposed, reference unmodified) and the 1e-13 solve still passes"""
+    import os
+
+    so = ROOT / "sundials_b200" / "lib" / "libsundials_b200gs.so"
+    assert so.exists()
+    env = dict(os.environ, LD_PRELOAD=str(so), B200GS_REPORT="1")
+    p = BIN / "test_sunlinsol_spgmr_b200"
+    # args of the reference CTest (spgmr/serial/CMakeLists.txt:35): n, gstype (2 = classical), pretype, maxl, tol, timing
+    r = subprocess.run([str(p), "100", "2", "1", "100", "1e-13", "0"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "FAIL" not in r.stdout
+    calls = [int(x.rsplit(":", 1)[1]) for x in r.stderr.splitlines() if "SUNClassicalGS_B200 calls" in x]
+    assert calls and calls[0] > 0, r.stderr[-500:]
+    # and without the preload the same program never reaches it
+    r0 = subprocess.run([str(p), "100", "2", "1", "100", "1e-13", "0"], capture_output=True, text=True, timeout=600)
+    assert r0.returncode == 0 and r0.stdout == r.stdout  # same printed solve, fused or not
+
+
+def test_reference_cuda_example_with_device_rhs_kernels():
+    """examples/cvode/cuda/cvAdvDiff_kry_cuda.cu, UNMODIFIED (shim header maps N_V*_Cuda -> N_V*_B200):
+    RHS / Jv are user CUDA kernels on the legacy default stream reading N_VGetDeviceArrayPointer, the
+    vector ops run on a user stream -- the only reference program that exercises NVECTOR_B200's
+    device mode with foreign kernels.  Every printed norm and every counter must equal the reference's
+    own committed output of the program on nvector_cuda (nst = 143, nfe = 206, nni = 203, nli = 225,
+    netf = 2).  Only the integer-workspace sizes leniw / leniwLS differ: N_VSpace reports liw = 1 per
+    vector like nvector_serial (serial:362-373), nvector_cuda reports 2 (cuda:749)."""
+    import re
+
+    r = _run("cvAdvDiff_kry_cuda_b200")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    want = (GOLD / "cvAdvDiff_kry_cuda.refcuda.out").read_text()
+    strip = lambda t: re.sub(r"(leniw(LS)?\s*=\s*)\d+", r"\1#", t)  # noqa: E731
+    assert strip(r.stdout) == strip(want), _first_diff(strip(r.stdout), strip(want))
+    assert "nst     =   143" in r.stdout and "nli     =   225" in r.stdout
+
+
 @pytest.mark.parametrize("tag", sorted(MANIFEST))
 def test_reference_program_output_identical_to_serial_golden(tag):
     e = MANIFEST[tag]
