@@ -4,25 +4,31 @@
 A *step* is one pass of the reference's N_Vector performance suite
 (benchmarks/nvector/test_nvector_performance.c: every standard, reduction, fused
 and vector-array op, 16 N_VLinearSum cases, 4 N_VScale cases, ...) over vectors
-of length 2^LOG2N per GPU with nvecs=8, nsums=4, fused ops ENABLED, called
-through the plugin boundary -- the `N_V*_B200` functions that sit in the
-SUNDIALS N_Vector_Ops table (include/nvector_b200.h).  Throughput is
-ALGORITHMIC bytes (SURVEY.md section 8d byte model: each distinct operand read
-once, each output written once) per second, summed over the suite.
+of length 2^LOG2N per GPU with nvecs=8, nsums=4, fused ops ENABLED.  The suite is
+a C driver (apps/nvector_perf/nvector_perf.c, a re-host of the reference harness)
+that reaches every op through `v->ops->nv...` -- the SUNDIALS ops table, the
+drop-in boundary -- exactly as the integrators do; the SAME compiled driver runs
+both arms (NVECTOR_B200 here, the reference's nvector_openmp under --impl reference).
+Throughput is ALGORITHMIC bytes (SURVEY.md section 8d byte model: each distinct
+operand read once, each output written once) per second, summed over the suite.
 
   value   suite GB/s with all operands resident in HBM (CUDA events, max over ranks)
-  e2e     same suite, but every step first copies the nvecs input vectors from
-          pinned host memory (N_VCopyToDevice_B200) and ends with a D2H read of a
-          result vector plus the reduction scalars
+  e2e     same suite, every step's nvecs input vectors uploaded from pinned host memory
+          (N_VCopyToDeviceAsync_B200 on the context's copy stream, double-buffered: the upload
+          of step k+1 overlaps the kernels of step k) and a result vector + scalars read back
   roofline  the dominant kernel by share of the step (k_scaleadd_rows<4>) timed
           with CUDA events, vs the measured HBM copy peak
   cpu_baseline  the reference's own nvector_openmp (all host threads) and
           nvector_serial (1 core) on a bounded sample of the same suite
+  legs    (printed LAST) compact record of the integrator / Gram-Schmidt / sweep legs
   --impl reference : the reference CPU implementation alone (driver's baseline arm)
+  --sweep          : BASELINE configs[2], lengths 2^16 .. 2^30 per GPU, CPU columns beside
 
 Multi-GPU (torchrun, one rank per GPU): weak scaling, each rank owns the local
 block of a contiguous 1-D partition (MPIPlusX pattern); streaming ops need no
-communication, every reduction does an NCCL allreduce of its scalars.
+communication, every reduction folds the ranks' partials inside its kernel over
+NVLink peer memory (ncclAllReduce as the fallback transport).  Before timing, a
+distributed exact-answer parity block runs on BOTH transports (dist_parity).
 """
 from __future__ import annotations
 
@@ -40,108 +46,64 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 NVECS, NSUMS = 8, 4
+V = C.c_void_p
 
 
 # --------------------------------------------------------------------------
-# the suite: (name, algorithmic bytes per element, callable) -- identical for
-# the B200 plugin (suffix _B200) and the reference generic dispatch (suffix "")
+# the suite: C driver over the ops table (apps/nvector_perf)
 # --------------------------------------------------------------------------
-def make_suite(api, vec):
-    """vec: dict of handles: X[8], Y[8], Z[8], S, T, W, ID, CN, YY[4][8], ZZ[4][8]"""
-    X, Y, Z, S, T, W, ID, CN = vec["X"], vec["Y"], vec["Z"], vec["S"], vec["T"], vec["W"], vec["ID"], vec["CN"]
-    YY, ZZ = vec["YY"], vec["ZZ"]
-    nv, ns = len(X), len(YY)
-    a, b = 0.37, -1.63
-    c8 = api.coefs([0.11 * (j + 1) * (-1) ** j for j in range(nv)])
-    c8_one = api.coefs([1.0] + [0.11 * (j + 1) for j in range(1, nv)])
-    c4 = api.coefs([0.21 * (j + 1) * (-1) ** j for j in range(ns)])
-    cs8 = api.coefs([1.0 + 0.01 * j for j in range(nv)])
-    aX, aY, aZ = api.varray(X), api.varray(Y), api.varray(Z)
-    aYS = api.varray([S] + Y[1:])  # fused in-place forms act on the scratch vector
-    aW = api.varray(Y)  # distinct weight vectors (byte model: 16 nv)
-    aYY, aZZ = api.varray2d(YY), api.varray2d(ZZ)
-    dots = (C.c_double * nv)()
-    nrm = (C.c_double * nv)()
-    res = {}
-    s = []
-
-    def op(name, bpe, fn):
-        s.append((name, bpe, fn))
-
-    # N_VLinearSum cases 1a..9 (test_nvector_performance.c:70-472); in-place forms
-    # run on scratch copies so the read-only inputs X, Y survive the step
-    op("N_VScale-2(copy)", 16, lambda: api.Scale(1.0, Y[0], S))
-    op("N_VLinearSum-1a", 24, lambda: api.LinearSum(1.0, X[0], 1.0, S, S))
-    op("N_VLinearSum-1b", 24, lambda: api.LinearSum(-1.0, X[0], 1.0, S, S))
-    op("N_VLinearSum-1c", 24, lambda: api.LinearSum(a, X[0], 1.0, S, S))
-    op("N_VLinearSum-2a", 24, lambda: api.LinearSum(1.0, S, 1.0, Y[0], S))
-    op("N_VLinearSum-2b", 24, lambda: api.LinearSum(1.0, S, -1.0, Y[0], S))
-    op("N_VLinearSum-2c", 24, lambda: api.LinearSum(1.0, S, b, Y[0], S))
-    op("N_VLinearSum-3", 24, lambda: api.LinearSum(1.0, X[0], 1.0, Y[0], Z[0]))
-    op("N_VLinearSum-4a", 24, lambda: api.LinearSum(1.0, X[1], -1.0, Y[1], Z[1]))
-    op("N_VLinearSum-4b", 24, lambda: api.LinearSum(-1.0, X[2], 1.0, Y[2], Z[2]))
-    op("N_VLinearSum-5a", 24, lambda: api.LinearSum(1.0, X[3], b, Y[3], Z[3]))
-    op("N_VLinearSum-5b", 24, lambda: api.LinearSum(a, X[4], 1.0, Y[4], Z[4]))
-    op("N_VLinearSum-6a", 24, lambda: api.LinearSum(-1.0, X[5], b, Y[5], Z[5]))
-    op("N_VLinearSum-6b", 24, lambda: api.LinearSum(a, X[6], -1.0, Y[6], Z[6]))
-    op("N_VLinearSum-7", 24, lambda: api.LinearSum(a, X[7], a, Y[7], Z[7]))
-    op("N_VLinearSum-8", 24, lambda: api.LinearSum(a, X[0], -a, Y[1], Z[0]))
-    op("N_VLinearSum-9", 24, lambda: api.LinearSum(a, X[1], b, Y[2], Z[1]))
-    op("N_VConst", 8, lambda: api.Const(1.5, T))
-    op("N_VProd", 24, lambda: api.Prod(X[2], Y[3], Z[2]))
-    op("N_VDiv", 24, lambda: api.Div(X[3], Y[4], Z[3]))
-    op("N_VScale-1(inplace)", 16, lambda: api.Scale(1.0009765625, S, S))
-    op("N_VScale-3(neg)", 16, lambda: api.Scale(-1.0, X[4], Z[4]))
-    op("N_VScale-4", 16, lambda: api.Scale(a, X[5], Z[5]))
-    op("N_VAbs", 16, lambda: api.Abs(X[6], Z[6]))
-    op("N_VInv", 16, lambda: api.Inv(X[7], Z[7]))
-    op("N_VAddConst", 16, lambda: api.AddConst(X[0], b, Z[0]))
-    op("N_VDotProd", 16, lambda: res.__setitem__("dot", api.DotProd(X[1], Y[1])))
-    op("N_VMaxNorm", 8, lambda: res.__setitem__("max", api.MaxNorm(X[2])))
-    op("N_VWrmsNorm", 16, lambda: res.__setitem__("wrms", api.WrmsNorm(X[3], W)))
-    op("N_VWrmsNormMask", 24, lambda: res.__setitem__("wrmsmask", api.WrmsNormMask(X[4], W, ID)))
-    op("N_VMin", 8, lambda: res.__setitem__("min", api.Min(X[5])))
-    op("N_VWL2Norm", 16, lambda: res.__setitem__("wl2", api.WL2Norm(X[6], W)))
-    op("N_VL1Norm", 8, lambda: res.__setitem__("l1", api.L1Norm(X[7])))
-    op("N_VCompare", 16, lambda: api.Compare(0.75, X[0], Z[0]))
-    op("N_VInvTest", 16, lambda: res.__setitem__("invtest", api.InvTest(X[1], Z[1])))
-    op("N_VConstrMask", 24, lambda: res.__setitem__("constr", api.ConstrMask(CN, X[2], Z[2])))
-    op("N_VMinQuotient", 16, lambda: res.__setitem__("minq", api.MinQuotient(X[3], Y[3])))
-    # fused (test_nvector_performance.c:1312-1700); -1/-2 are the in-place forms
-    op("N_VLinearCombination-1", 8 * (nv + 1), lambda: api.LinearCombination(nv, c8_one, aYS, S))
-    op("N_VLinearCombination-2", 8 * (nv + 1), lambda: api.LinearCombination(nv, c8, aYS, S))
-    op("N_VLinearCombination-3", 8 * (nv + 1), lambda: api.LinearCombination(nv, c8, aX, T))
-    op("N_VScaleAddMulti-1", 8 * (2 * nv + 1), lambda: api.ScaleAddMulti(nv, c8, X[0], aZ, aZ))
-    op("N_VScaleAddMulti-2", 8 * (2 * nv + 1), lambda: api.ScaleAddMulti(nv, c8, X[1], aY, aZ))
-    op("N_VDotProdMulti", 8 * (nv + 1), lambda: api.DotProdMulti(nv, X[2], aY, dots))
-    # vector arrays (:1700-2690)
-    op("N_VLinearSumVectorArray", 24 * nv, lambda: api.LinearSumVectorArray(nv, a, aX, b, aY, aZ))
-    op("N_VScaleVectorArray", 16 * nv, lambda: api.ScaleVectorArray(nv, cs8, aX, aZ))
-    op("N_VConstVectorArray", 8 * nv, lambda: api.ConstVectorArray(nv, 0.5, aZ))
-    op("N_VWrmsNormVectorArray", 16 * nv, lambda: api.WrmsNormVectorArray(nv, aX, aW, nrm))
-    op("N_VWrmsNormMaskVectorArray", 8 * (2 * nv + 1), lambda: api.WrmsNormMaskVectorArray(nv, aX, aW, ID, nrm))
-    op("N_VScaleAddMultiVectorArray", 8 * (nv + 2 * nv * ns),
-       lambda: api.ScaleAddMultiVectorArray(nv, ns, c4, aX, aYY, aZZ))
-    op("N_VLinearCombinationVectorArray", 8 * (nv * ns + nv),
-       lambda: api.LinearCombinationVectorArray(nv, ns, c4, aYY, aZ))
-    # local reductions (no communication even on a distributed vector)
-    op("N_VDotProdLocal", 16, lambda: res.__setitem__("dotl", api.DotProdLocal(X[4], Y[4])))
-    op("N_VMaxNormLocal", 8, lambda: res.__setitem__("maxl", api.MaxNormLocal(X[5])))
-    op("N_VWSqrSumLocal", 16, lambda: res.__setitem__("wsql", api.WSqrSumLocal(X[6], W)))
-    op("N_VDotProdMultiLocal", 8 * (nv + 1), lambda: api.DotProdMultiLocal(nv, X[7], aY, dots))
-    # the step's result: a checksum of an output vector (read back by the host)
-    op("N_VWrmsNorm(result)", 16, lambda: res.__setitem__("result", api.WrmsNorm(Z[1], W)))
-    keep = (c8, c8_one, c4, cs8, aX, aY, aZ, aYS, aW, aYY, aZZ, dots, nrm)
-    return s, res, keep
+def load_perf():
+    so = ROOT / "apps" / "nvector_perf" / "_build" / "libnvector_perf.so"
+    if not so.exists():
+        raise FileNotFoundError(f"{so} missing (run `make -C apps/nvector_perf` where the SUNDIALS headers exist)")
+    lib = C.CDLL(str(so))
+    Vp = C.POINTER(V)
+    lib.nvperf_create.restype, lib.nvperf_create.argtypes = V, [Vp, Vp, Vp, V, V, V, V, V, Vp, Vp, C.c_int, C.c_int]
+    lib.nvperf_destroy.restype, lib.nvperf_destroy.argtypes = None, [V]
+    lib.nvperf_num_ops.restype = C.c_int
+    lib.nvperf_op_name.restype, lib.nvperf_op_name.argtypes = C.c_char_p, [C.c_int]
+    lib.nvperf_op_bytes_per_elt.restype, lib.nvperf_op_bytes_per_elt.argtypes = C.c_double, [V, C.c_int]
+    lib.nvperf_op_returns_scalar.restype, lib.nvperf_op_returns_scalar.argtypes = C.c_int, [C.c_int]
+    lib.nvperf_run_op.restype, lib.nvperf_run_op.argtypes = None, [V, C.c_int, C.c_int]
+    lib.nvperf_run_step.restype, lib.nvperf_run_step.argtypes = None, [V, C.c_int]
+    lib.nvperf_result.restype, lib.nvperf_result.argtypes = C.c_double, [V, C.c_int]
+    lib.nvperf_error.restype, lib.nvperf_error.argtypes = C.c_int, [V]
+    return lib
 
 
-def fill_inputs(rng, n):
-    import numpy as np
+class Suite:
+    """one nvperf suite over a dict of vector handles (see alloc_vectors)"""
 
-    def pm(lo, hi):
-        return rng.uniform(lo, hi, n) * (rng.integers(0, 2, n) * 2 - 1)
+    def __init__(self, perf, vec, X=None):
+        self.perf = perf
+        X = X or vec["X"]
+        nv, ns = len(X), len(vec["YY"])
+        arr = lambda hs: (V * len(hs))(*hs)  # noqa: E731
+        self._keep = (arr(X), arr(vec["Y"]), arr(vec["Z"]), arr([h for row in vec["YY"] for h in row]),
+                      arr([h for row in vec["ZZ"] for h in row]))
+        self.h = perf.nvperf_create(self._keep[0], self._keep[1], self._keep[2], vec["S"], vec["T"], vec["W"], vec["ID"],
+                                    vec["CN"], self._keep[3], self._keep[4], nv, ns)
+        if not self.h:
+            raise RuntimeError("nvperf_create failed (fused ops not enabled on the vector?)")
+        self.nops = perf.nvperf_num_ops()
+        self.names = [perf.nvperf_op_name(i).decode() for i in range(self.nops)]
+        self.bpe = [perf.nvperf_op_bytes_per_elt(self.h, i) for i in range(self.nops)]
+        self.scalar = [bool(perf.nvperf_op_returns_scalar(i)) for i in range(self.nops)]
+        self.bytes_per_elt_step = sum(self.bpe)
 
-    return pm, np
+    def step(self, k=1):
+        self.perf.nvperf_run_step(self.h, k)
+
+    def op(self, i, reps=1):
+        self.perf.nvperf_run_op(self.h, i, reps)
+
+    def result(self, name):
+        return self.perf.nvperf_result(self.h, self.names.index(name))
+
+    def check(self):
+        e = self.perf.nvperf_error(self.h)
+        if e:
+            raise RuntimeError(f"a fused op of the suite returned error {e}")
 
 
 def alloc_vectors(newvec, nv=NVECS, ns=NSUMS):
@@ -158,6 +120,25 @@ def all_handles(vec):
     for row in vec["YY"] + vec["ZZ"]:
         out += row
     return out
+
+
+def base_arrays(n, seed):
+    """Seeded synthetic data, mirroring N_VRand / N_VRandZeroOne / N_VRandConstraints of the reference
+    benchmark (test_nvector_performance.c:2751-2800) with a FIXED seed: signed values away from 0
+    (divisors), positive weights, a 0/1 mask, constraints in {-2..2}.  Vector i of the suite holds
+    scale(i) * u -- cheap to build for 91 vectors on either arm, and identical on both arms."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(0.5, 1.5, n) * (rng.integers(0, 2, n) * 2 - 1)
+    w = rng.uniform(0.5, 1.5, n)
+    idm = rng.integers(0, 2, n).astype(np.float64)
+    cn = rng.integers(-2, 3, n).astype(np.float64)
+    return u, w, idm, cn
+
+
+def vec_scale(i):
+    return 0.75 + 0.5 * ((i * 0.6180339887498949) % 1.0)
 
 
 # --------------------------------------------------------------------------
@@ -260,12 +241,26 @@ class LegSampler:
 
 
 # --------------------------------------------------------------------------
-# reference CPU arm (the one place bench.py executes oracle/_ref)
+# reference libraries.  load_host: the unmodified host framework NVECTOR_B200 plugs into
+# (baseline/_ref: core, solvers, integrators).  load_reference: + the reference's CPU vectors
+# (oracle/_ref) -- the ONE place bench.py executes oracle/, and only in the CPU legs.
 # --------------------------------------------------------------------------
+def load_host():
+    so = ROOT / "baseline" / "_ref" / "lib" / "libsundials_host.so"
+    if not so.exists():
+        raise FileNotFoundError(f"{so} missing (build with `make -C baseline` where /root/reference exists)")
+    lib = C.CDLL(str(so), mode=C.RTLD_GLOBAL)
+    lib.SUNContext_Create.restype, lib.SUNContext_Create.argtypes = C.c_int, [C.c_int, C.POINTER(C.c_void_p)]
+    lib.N_VGetArrayPointer.restype, lib.N_VGetArrayPointer.argtypes = C.POINTER(C.c_double), [C.c_void_p]
+    lib.N_VDestroy.restype, lib.N_VDestroy.argtypes = None, [C.c_void_p]
+    return lib
+
+
 def load_reference():
     so = ROOT / "oracle" / "_ref" / "lib" / "libsundials_ref.so"
     if not so.exists():
         raise FileNotFoundError(f"{so} missing (build with `make -C oracle ref` where /root/reference exists)")
+    load_host()
     lib = C.CDLL(str(so), mode=C.RTLD_GLOBAL)
     lib.SUNContext_Create.restype, lib.SUNContext_Create.argtypes = C.c_int, [C.c_int, C.POINTER(C.c_void_p)]
     lib.N_VNew_OpenMP.restype, lib.N_VNew_OpenMP.argtypes = C.c_void_p, [C.c_int64, C.c_int, C.c_void_p]
@@ -273,71 +268,80 @@ def load_reference():
     lib.N_VEnableFusedOps_OpenMP.restype, lib.N_VEnableFusedOps_OpenMP.argtypes = C.c_int, [C.c_void_p, C.c_int]
     lib.N_VEnableFusedOps_Serial.restype, lib.N_VEnableFusedOps_Serial.argtypes = C.c_int, [C.c_void_p, C.c_int]
     lib.N_VGetArrayPointer.restype, lib.N_VGetArrayPointer.argtypes = C.POINTER(C.c_double), [C.c_void_p]
+    lib.N_VDestroy.restype, lib.N_VDestroy.argtypes = None, [C.c_void_p]
     return lib
 
 
-def run_reference_suite(log2n: int, steps: int, warmup: int, threads: int, budget_s: float = 150.0):
-    """Time the reference's own CPU vector on the suite.  threads > 1: nvector_openmp,
-    threads == 1: nvector_serial.  Returns (GB/s, ms_per_step, sample description)."""
+def host_mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
+
+
+def cpu_vectors(lib, sctx, n, threads, nv=NVECS, ns=NSUMS, seed=1234):
+    """the suite's vectors on the reference's own CPU vector: nvector_openmp (threads > 1) or
+    nvector_serial, fused ops enabled, the same data as the B200 arm (base_arrays / vec_scale)"""
     import numpy as np
-
-    from sundials_b200.plugin import Api
-
-    lib = load_reference()
-    ctx = C.c_void_p()
-    assert lib.SUNContext_Create(0, C.byref(ctx)) == 0
-    api = Api(lib, "")
-    n = 1 << log2n
-    rng = np.random.default_rng(1234)
 
     def newvec():
         if threads > 1:
-            v = lib.N_VNew_OpenMP(n, threads, ctx)
+            v = lib.N_VNew_OpenMP(n, threads, sctx)
             lib.N_VEnableFusedOps_OpenMP(v, 1)
         else:
-            v = lib.N_VNew_Serial(n, ctx)
+            v = lib.N_VNew_Serial(n, sctx)
             lib.N_VEnableFusedOps_Serial(v, 1)
+        assert v, "reference vector constructor failed (out of host memory?)"
         return v
 
-    vec = alloc_vectors(newvec)
-    _init_values(vec, lambda v: np.ctypeslib.as_array(lib.N_VGetArrayPointer(v), shape=(n,)), rng, n)
-    suite, res, _keep = make_suite(api, vec)
-    bytes_per_step = sum(b for _, b, _ in suite) * n
+    vec = alloc_vectors(newvec, nv, ns)
+    view = lambda v: np.ctypeslib.as_array(lib.N_VGetArrayPointer(v), shape=(n,))  # noqa: E731
+    u, w, idm, cn = base_arrays(n, seed)
+    for i, v in enumerate(all_handles(vec)):
+        np.multiply(u, vec_scale(i), out=view(v))
+    np.multiply(w, vec_scale(1), out=view(vec["W"]))
+    view(vec["ID"])[...] = idm
+    view(vec["CN"])[...] = cn
+    return vec
 
-    def step():
-        for _, _, fn in suite:
-            fn()
 
+def free_vectors(lib, vec):
+    for v in all_handles(vec):
+        lib.N_VDestroy(v)
+
+
+def run_reference_suite(log2n: int, steps: int, warmup: int, threads: int, budget_s: float = 150.0):
+    """Time the reference's own CPU vector on the suite (the same C driver as the B200 arm).
+    threads > 1: nvector_openmp, threads == 1: nvector_serial.
+    Returns (GB/s, ms_per_step, sample description, steps run, result checksum)."""
+    lib = load_reference()
+    perf = load_perf()
+    sctx = C.c_void_p()
+    assert lib.SUNContext_Create(0, C.byref(sctx)) == 0
+    n = 1 << log2n
+    vec = cpu_vectors(lib, sctx, n, threads)
+    suite = Suite(perf, vec)
+    bytes_per_step = suite.bytes_per_elt_step * n
     t0 = time.perf_counter()
-    step()
+    suite.step(1)
     first = time.perf_counter() - t0
     # bound the run: fewer timed steps if the box is slow (never fewer than 1)
     warmup = min(warmup, max(0, int(budget_s * 0.2 / first) - 1))
     steps_run = max(1, min(steps, int(budget_s * 0.8 / first)))
-    for _ in range(warmup):
-        step()
+    suite.step(warmup)
     t0 = time.perf_counter()
-    for _ in range(steps_run):
-        step()
+    suite.step(steps_run)
     dt = (time.perf_counter() - t0) / steps_run
+    suite.check()
+    checksum = suite.result("N_VWrmsNorm(result)")
     kind = f"nvector_openmp({threads} threads)" if threads > 1 else "nvector_serial(1 core)"
-    sample = (f"{kind}, same {len(suite)}-op suite, fused ops enabled, length 2^{log2n} per vector "
-              f"(bounded sample), {steps_run} timed steps after {warmup + 1} warm-up")
-    return bytes_per_step / dt / 1e9, dt * 1e3, sample, steps_run
-
-
-def _init_values(vec, host_view, rng, n):
-    """Fill every vector with benign seeded data (inputs away from 0, 0/1 mask,
-    constraints in {-2..2}) -- mirrors N_VRand / N_VRandZeroOne / N_VRandConstraints
-    of the reference benchmark but with a fixed seed."""
-    import numpy as np
-
-    for v in all_handles(vec):
-        a = host_view(v)
-        a[...] = rng.uniform(0.5, 1.5, n) * (rng.integers(0, 2, n) * 2 - 1)
-    host_view(vec["W"])[...] = rng.uniform(0.5, 1.5, n)
-    host_view(vec["ID"])[...] = rng.integers(0, 2, n).astype(np.float64)
-    host_view(vec["CN"])[...] = rng.integers(-2, 3, n).astype(np.float64)
+    sample = (f"{kind}, same {suite.nops}-op suite (C driver over the ops table), fused ops enabled, length "
+              f"2^{log2n} per vector, {steps_run} timed steps after {warmup + 1} warm-up")
+    free_vectors(lib, vec)
+    return bytes_per_step / dt / 1e9, dt * 1e3, sample, steps_run, checksum
 
 
 def run_diffusion(ctx, world, args):
@@ -429,26 +433,158 @@ def run_ar3d_cpu_reference(n=64, tf=0.05):
             "ns_per_unknown_per_step": round(dt / max(nst, 1) / (3 * n ** 3) * 1e9, 3)}
 
 
+def run_cvdiurnal():
+    """BASELINE config 2: the reference's examples/cvode/serial/cvDiurnal_kry.c, unmodified, on
+    NVECTOR_B200 (host-coherent pinned mode: the example's RHS runs on the host through
+    N_VGetArrayPointer) against the same source on nvector_serial.  N = 200 unknowns: launch-latency
+    bound by construction -- reported honestly ("even though slower")."""
+    b200 = ROOT / "baseline" / "_ref" / "bin" / "cvDiurnal_kry_b200"
+    ser = ROOT / "oracle" / "_ref" / "bin" / "cvDiurnal_kry_serial"
+    if not b200.exists():
+        return {"unavailable": f"{b200} missing"}
+
+    def best(exe, reps):
+        t, out = 1e30, ""
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+            t = min(t, time.perf_counter() - t0)
+            out = r.stdout
+        return t, out
+
+    tb, ob = best(b200, 2)
+    leg = {"workload": "CVODE cvDiurnal_kry (2-species diurnal kinetics, BDF + SPGMR, N = 200), whole-program wall "
+                       "time, best of 2; NVECTOR_B200 in its host-coherent pinned mode (every op synchronises)",
+           "b200_pinned_s": round(tb, 3)}
+    gold = ROOT / "tests" / "golden" / "examples" / "cvDiurnal_kry.out"
+    if gold.exists():
+        leg["stdout_identical_to_serial_golden"] = (ob == gold.read_text())
+    if ser.exists():
+        ts, os_ = best(ser, 3)
+        leg["serial_1core_s"] = round(ts, 3)
+        leg["stdout_identical_to_serial_run"] = (ob == os_)
+    return leg
+
+
+def dist_parity(P, lib, ctx, rank, world, dist, torch):
+    """world > 1: exact-answer checks through N_V*_B200 on DISTRIBUTED vectors, on both transports
+    (peer-memory fold inside the reduction kernel, and ncclAllReduce), bit-equal between the transports
+    and across the ranks.  Known answers in the style of the reference's MPI vector tests
+    (test/unit_tests/nvector/test_nvector.c: global-length answers; Test_N_VDotProdMultiAllReduce
+    :5663-5794): exactly representable data, one sentinel per rank for max / min, a zero on the last
+    rank for N_VInvTest, a 3-wide N_VDotProdMulti, the fused linear-combination + norm."""
+    import numpy as np
+
+    fails, checks, bits = [], 0, {}
+    transports = []
+    for p2p in (1, 0):
+        lib.b200vec_ctx_set_tuning(ctx, b"p2p", p2p)
+        lib.b200vec_comm_transport.restype = C.c_char_p
+        tname = lib.b200vec_comm_transport(ctx).decode()
+        transports.append(tname)
+        got = []
+        for n in (1000, 1 << 20):       # exact-order path and the tree path
+            ng = n * world
+
+            def mk(val):
+                v = P.new(n, ctx, P.DEVICE, fused=True)
+                assert lib.N_VMakeDistributed_B200(v, ng) == 0
+                P.Const(val, v)
+                return v
+
+            x, y, z = mk(2.0), mk(0.5), mk(0.0)
+            exp = [("N_VGetLength", float(P.GetLength(x)), float(ng)),
+                   ("N_VDotProd", P.DotProd(x, y), float(ng)),
+                   ("N_VL1Norm", P.L1Norm(x), 2.0 * ng),
+                   ("N_VWrmsNorm", P.WrmsNorm(x, y), 1.0),
+                   ("N_VWL2Norm", P.WL2Norm(x, y), float(np.sqrt(float(ng)))),
+                   ("N_VDotProdLocal", P.DotProdLocal(x, y), float(n)),
+                   ("N_VInvTest(no zero)", float(P.InvTest(x, z)), 1.0),
+                   ("N_VMinQuotient", P.MinQuotient(x, y), 4.0)]
+            d = (C.c_double * 3)()
+            Y3 = P.varray([x, y, x])
+            assert P.DotProdMulti(3, x, Y3, d) == 0
+            exp += [("N_VDotProdMulti[0]", d[0], 4.0 * ng), ("N_VDotProdMulti[1]", d[1], float(ng)),
+                    ("N_VDotProdMulti[2]", d[2], 4.0 * ng)]
+            sq = C.c_double()
+            lib.N_VLinearCombinationSqNorm_B200.restype = C.c_int
+            lib.N_VLinearCombinationSqNorm_B200.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(V), V,
+                                                            C.POINTER(C.c_double)]
+            assert lib.N_VLinearCombinationSqNorm_B200(3, P.coefs([1.0, 2.0, -1.0]), P.varray([z, y, x]), z,
+                                                       C.byref(sq)) == 0      # z = 1/2 + 1 - 2 = -1/2
+            exp.append(("N_VLinearCombinationSqNorm", sq.value, 0.25 * ng))
+            # sentinels: rank r plants +(10 + r) and -(20 + r); the last rank plants a zero
+            h = P.host(x, n)
+            P.from_device(x)
+            h[7 + rank] = 10.0 + rank
+            h[n - 9 - rank] = -(20.0 + rank)
+            P.to_device(x)
+            exp += [("N_VMaxNorm", P.MaxNorm(x), 20.0 + world - 1), ("N_VMin", P.Min(x), -(20.0 + world - 1)),
+                    ("N_VMaxNormLocal", P.MaxNormLocal(x), 20.0 + rank)]
+            if rank == world - 1:
+                h[n // 2] = 0.0
+                P.to_device(x)
+            exp.append(("N_VInvTest(zero on last rank)", float(P.InvTest(x, z)), 0.0))
+            for name, g, w in exp:
+                checks += 1
+                got.append(g)
+                if g != w:
+                    fails.append(f"{tname} n={n} {name}: got {g!r} want {w!r}")
+            for v in (x, y, z):
+                P.Destroy(v)
+        bits[tname] = np.array(got, dtype=np.float64)
+    lib.b200vec_ctx_set_tuning(ctx, b"p2p", 1)
+    # identical bits on both transports and on every rank
+    a = bits[transports[0]]
+    if len(set(transports)) == 2 and not np.array_equal(a.view(np.uint64), bits[transports[1]].view(np.uint64)):
+        fails.append("results differ between the transports")
+    skip = {i for i in range(len(a)) if i % 16 in (5, 14)}   # the *Local values differ by rank by design
+    t = torch.tensor(a, dtype=torch.float64, device="cuda")
+    allr = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(allr, t)
+    for r in range(world):
+        b = allr[r].cpu().numpy()
+        if any(a[i].tobytes() != b[i].tobytes() for i in range(len(a)) if i not in skip):
+            fails.append(f"rank {rank} and rank {r} disagree")
+    nf = torch.tensor([len(fails)], device="cuda")
+    dist.all_reduce(nf)
+    return {"ok": int(nf.item()) == 0, "world": world, "transports": transports, "checks_per_rank": checks,
+            "failures": fails[:4]}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    log2n = min(args.log2n, args.cpu_log2n)
+    log2n = args.log2n
+    # the suite holds 91 vectors: run the TRUE length when the host has the memory for it
+    need = 91 * (8 << log2n) * 1.15
+    note = None
+    while log2n > 16 and need > host_mem_available_bytes() * 0.8:
+        log2n -= 1
+        need /= 2
+        note = f"host memory allows 2^{log2n} only"
     try:
-        gbs, ms, sample, steps_run = run_reference_suite(log2n, args.steps, args.warmup, threads)
+        gbs, ms, sample, steps_run, checksum = run_reference_suite(log2n, args.steps, args.warmup, threads)
     except FileNotFoundError as e:
         print(json.dumps({"impl": "reference", "unavailable": str(e)}))
         return 0
+    cfg_args = argparse.Namespace(**vars(args))
+    cfg_args.log2n = log2n
     line = {
         "impl": "reference", "metric": "N_Vector op suite throughput (algorithmic GB/s)", "value": round(gbs, 2),
-        "unit": "GB/s", "n_gpus": args.gpus, "steps": steps_run, "warmup": args.warmup,
+        "unit": "GB/s", "n_gpus": args.gpus, "gpus_used": 0, "host_cores": threads, "ranks_run": 1,
+        "steps": steps_run, "warmup": args.warmup,
         "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args),
+        "config": workload_config(cfg_args),
         "cpu_baseline": {"value": round(gbs, 2), "unit": "GB/s", "cores": threads, "kind": "reference",
                          "sample": sample},
         "e2e": {"value": round(gbs, 2), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "result_checksum": checksum,
+        "note": note or "n_gpus is the launch shape the driver asked for; this arm runs on the host cores of rank 0 "
+                        "only (gpus_used 0), on the same per-GPU workload",
     }
     print(json.dumps(line))
     return 0
@@ -460,16 +596,162 @@ def workload_config(args):
                     f"length 2^{args.log2n} per GPU, nvecs={NVECS}, nsums={NSUMS}, fused ops enabled",
         "length_per_gpu": 1 << args.log2n,
         "nvecs": NVECS, "nsums": NSUMS,
+        "driver": "apps/nvector_perf (C loop over the N_Vector ops table, as benchmarks/nvector does)",
         "partition": "contiguous 1-D block per GPU (MPIPlusX pattern); reductions fold the ranks' partials over "
                      "NVLink peer memory inside the reduction kernel (NCCL allreduce as fallback); no other communication",
-        "cache": "inputs larger than L2: every op streams >= 128 MiB per operand (126 MB L2), "
-                 "91 distinct vectors (11.4 GiB) rotate through the suite",
+        "cache": f"inputs {'larger than' if args.log2n >= 24 else 'vs'} L2: every op streams {(8 << args.log2n) / 2**20:g} MiB per "
+                 f"operand (126 MB L2), 91 distinct vectors ({91 * (8 << args.log2n) / 2**30:.1f} GiB) rotate through the suite",
     }
 
 
 # --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
+def b200_vectors(P, lib, ctx, n, world, rank, nv=NVECS, ns=NSUMS, keep_host_x=True, seed=1234):
+    """the suite's vectors on NVECTOR_B200 (device memory), same data as cpu_vectors(): four base
+    arrays are uploaded once and every vector is scale(i) * base, formed ON the device by N_VScale;
+    only the X vectors (re-uploaded by the e2e leg) keep a pinned host mirror."""
+    import numpy as np
+
+    def newvec():
+        v = P.new(n, ctx, P.DEVICE, fused=True)
+        if world > 1:
+            assert lib.N_VMakeDistributed_B200(v, n * world) == 0
+        return v
+
+    vec = alloc_vectors(newvec, nv, ns)
+    u, w, idm, cn = base_arrays(n, seed + rank)
+    base = newvec()
+    hb = P.host(base, n)
+
+    def upload(arr):
+        hb[...] = arr
+        P.to_device(base)
+
+    upload(u)
+    xs = set(vec["X"])
+    for i, v in enumerate(all_handles(vec)):
+        if v in (vec["W"], vec["ID"], vec["CN"]):
+            continue
+        P.Scale(vec_scale(i), base, v)
+        if keep_host_x and v in xs:
+            np.multiply(u, vec_scale(i), out=P.host(v, n))
+    upload(w)
+    P.Scale(vec_scale(1), base, vec["W"])
+    upload(idm)
+    P.Scale(1.0, base, vec["ID"])
+    upload(cn)
+    P.Scale(1.0, base, vec["CN"])
+    lib.b200vec_ctx_sync(ctx)
+    P.Destroy(base)
+    return vec
+
+
+def run_sweep(P, lib, perf, ctx, world, rank, dist, torch, peak, lengths, cpu_lengths, with_cpu):
+    """BASELINE configs[2]: one representative op per kernel class over vector lengths 2^16 .. 2^30
+    per GPU (C driver, CUDA events, the API call incl. the host hand-off for the scalar ops), and the
+    reference's nvector_serial / nvector_openmp on this box's host cores at the same lengths (bounded)."""
+    classes = ["N_VLinearSum-9", "N_VScale-4", "N_VConst", "N_VDotProd", "N_VMaxNorm", "N_VWrmsNormMask",
+               "N_VLinearCombination-3", "N_VScaleAddMulti-2", "N_VDotProdMulti"]
+    out = {"ops": classes, "lengths": {}, "timing": "C driver loop, CUDA events; reps back to back on one operand set "
+           "(> L2 from 2^22 x 3 operands on; smaller lengths are L2 / launch-latency figures)"}
+    free, _ = torch.cuda.mem_get_info()
+    for L in lengths:
+        n = 1 << L
+        nv = 8
+        while nv > 2 and (5 * nv + 5) * n * 8 > free * 0.85:
+            nv //= 2
+        if (5 * nv + 5) * n * 8 > free * 0.85:
+            out["lengths"][f"2^{L}"] = {"skipped": "does not fit HBM"}
+            continue
+        newvec_count = [0]
+
+        def newvec():
+            newvec_count[0] += 1
+            v = P.new(n, ctx, P.DEVICE, fused=True)
+            if world > 1:
+                assert lib.N_VMakeDistributed_B200(v, n * world) == 0
+            P.Const(0.75 + 0.01 * (newvec_count[0] % 17), v)
+            return v
+
+        X, Y, Z = [newvec() for _ in range(nv)], [newvec() for _ in range(nv)], [newvec() for _ in range(nv)]
+        vec = {"X": X, "Y": Y, "Z": Z, "S": newvec(), "T": newvec(), "W": newvec(), "ID": newvec(), "CN": newvec(),
+               "YY": [Y], "ZZ": [Z]}
+        suite = Suite(perf, vec)
+        row = {}
+        for name in classes:
+            i = suite.names.index(name)
+            suite.op(i, 3)
+            torch.cuda.synchronize()
+            reps = int(max(5, min(200, 40e9 / (suite.bpe[i] * n))))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if dist is not None:
+                dist.barrier()
+            e0.record()
+            suite.op(i, reps)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / reps * 1e3
+            if dist is not None:
+                t = torch.tensor([us], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                us = float(t.item())
+            gbs = suite.bpe[i] * n / us / 1e3
+            row[name] = {"us": round(us, 2), "GBs": round(gbs, 1), "frac": round(gbs / peak, 3)}
+        suite.check()
+        out["lengths"][f"2^{L}"] = {"nvecs": nv, "ops": row}
+        for v in X + Y + Z + [vec["S"], vec["T"], vec["W"], vec["ID"], vec["CN"]]:
+            P.Destroy(v)
+        lib.b200vec_ctx_sync(ctx)
+    if with_cpu and rank == 0:
+        try:
+            ref = load_reference()
+            sctx = C.c_void_p()
+            assert ref.SUNContext_Create(0, C.byref(sctx)) == 0
+            threads = os.cpu_count() or 1
+            cpu = {"cores": threads, "lengths": {}}
+            for L in cpu_lengths:
+                n = 1 << L
+                if 45 * n * 8 * 1.2 > host_mem_available_bytes() * 0.7:
+                    cpu["lengths"][f"2^{L}"] = {"skipped": "host memory"}
+                    continue
+                row = {}
+                for kind, th in (("serial", 1), ("openmp", threads)):
+                    import numpy as np
+
+                    def newvec():
+                        v = ref.N_VNew_OpenMP(n, th, sctx) if th > 1 else ref.N_VNew_Serial(n, sctx)
+                        (ref.N_VEnableFusedOps_OpenMP if th > 1 else ref.N_VEnableFusedOps_Serial)(v, 1)
+                        np.ctypeslib.as_array(ref.N_VGetArrayPointer(v), shape=(n,))[...] = 0.75
+                        return v
+
+                    X, Y, Z = [newvec() for _ in range(8)], [newvec() for _ in range(8)], [newvec() for _ in range(8)]
+                    vec = {"X": X, "Y": Y, "Z": Z, "S": newvec(), "T": newvec(), "W": newvec(), "ID": newvec(),
+                           "CN": newvec(), "YY": [Y], "ZZ": [Z]}
+                    suite = Suite(perf, vec)
+                    for name in classes:
+                        i = suite.names.index(name)
+                        suite.op(i, 1)
+                        reps = int(max(2, min(200, 1.5e9 / (suite.bpe[i] * n))))
+                        t0 = time.perf_counter()
+                        suite.op(i, reps)
+                        us = (time.perf_counter() - t0) / reps * 1e6
+                        row.setdefault(name, {})[kind] = {"us": round(us, 1), "GBs": round(suite.bpe[i] * n / us / 1e3, 2)}
+                    for v in X + Y + Z + [vec["S"], vec["T"], vec["W"], vec["ID"], vec["CN"]]:
+                        ref.N_VDestroy(v)
+                cpu["lengths"][f"2^{L}"] = row
+            out["cpu"] = cpu
+        except Exception as e:  # reported, never required
+            out["cpu"] = {"unavailable": f"{type(e).__name__}: {e}"}
+    # summary: how many of the 9 classes reach 0.8 of the measured peak, and the scalar-op latency floor
+    summ = {}
+    for key, val in out["lengths"].items():
+        if "ops" in val:
+            summ[key] = sum(1 for o in val["ops"].values() if o["frac"] >= 0.8)
+    out["classes_ge_0.8_of_peak"] = summ
+    return out
+
+
 def b200_arm(args):
     import numpy as np
     import torch
@@ -500,7 +782,11 @@ def b200_arm(args):
 
     lib = _lib.load()
     P = B200Plugin()
+    perf = load_perf()
     n = 1 << args.log2n
+    for name, res, argt in (("N_VCopyToDeviceAsync_B200", None, [V]), ("N_VCopyJoin_B200", None, [V])):
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, argt
 
     # one execution context per rank on the legacy stream (+ NCCL communicator)
     ctx = C.c_void_p()
@@ -514,48 +800,36 @@ def b200_arm(args):
         idbuf = (C.c_ubyte * _lib.UNIQUE_ID_BYTES).from_buffer_copy(bytes(t.cpu().tolist()))
         _lib.check(lib.b200vec_comm_init(ctx, idbuf, rank, world), "comm_init")
 
-    def newvec():
-        v = P.new(n, ctx, P.DEVICE, fused=True)
-        if world > 1:
-            assert lib.N_VMakeDistributed_B200(v, n * world) == 0
-        return v
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
-    vec = alloc_vectors(newvec)
-    rng = np.random.default_rng(1234 + rank)
-    # initialise through the plugin: pinned host mirror -> N_VCopyToDevice; only the
-    # nvecs input vectors X keep their host mirror (the e2e leg re-uploads them)
-    keep_host = set(vec["X"]) | {vec["Z"][1]}
-    for v in all_handles(vec):
-        a = P.host(v, n)
-        a[...] = rng.uniform(0.5, 1.5, n) * (rng.integers(0, 2, n) * 2 - 1)
-        if v == vec["W"]:
-            a[...] = np.abs(a)
-        elif v == vec["ID"]:
-            a[...] = rng.integers(0, 2, n)
-        elif v == vec["CN"]:
-            a[...] = rng.integers(-2, 3, n)
-        P.to_device(v)
-        if v not in keep_host:
-            P.drop_host(v)
-    suite, res, _keep = make_suite(P, vec)
-    bytes_per_step = sum(b for _, b, _ in suite) * n
+    # ---- distributed exact-answer parity on both transports, before anything is timed
+    parity = None
+    if world > 1:
+        try:
+            parity = dist_parity(P, lib, ctx, rank, world, dist, torch)
+        except Exception as e:
+            parity = {"ok": False, "world": world, "error": f"{type(e).__name__}: {e}"}
 
-    def step():
-        for _, _, fn in suite:
-            fn()
+    vec = b200_vectors(P, lib, ctx, n, world, rank)
+    suite = Suite(perf, vec)
+    bytes_per_step = suite.bytes_per_elt_step * n
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, k):
-        """k steps bracketed by barrier+sync, CUDA events on the launching (legacy) stream."""
+    def timed(fn):
+        """fn() bracketed by barrier+sync, CUDA events on the launching (legacy) stream, max over ranks."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for _ in range(k):
-            fn()
+        fn()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -563,113 +837,108 @@ def b200_arm(args):
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms / k
+        return ms
 
-    # ---- value: operands resident in HBM
-    for _ in range(args.warmup):
-        step()
+    # ---- value: operands resident in HBM; K steps in ONE call of the C driver
+    suite.step(args.warmup)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     lib.b200vec_ctx_set_tuning(ctx, b"count_launches", 1)
-    ms_step = timed(step, args.steps)
+    ms_step = timed(lambda: suite.step(args.steps)) / args.steps
     launches = int(lib.b200vec_ctx_launch_count(ctx))
     lib.b200vec_ctx_set_tuning(ctx, b"count_launches", 0)
-    result_value = res.get("result")
+    suite.check()
+    result_value = suite.result("N_VWrmsNorm(result)")
 
-    # ---- e2e: H2D of the nvecs input vectors + suite + D2H of a result vector and scalars
+    # ---- e2e: every step uploads the nvecs input vectors from pinned host memory and reads a result
+    # vector + the scalars back.  Double-buffered: two device copies of X; the upload of step k+1 runs on
+    # the context's copy stream while the kernels of step k run; the first upload is not overlapped and
+    # is inside the timed region, so K uploads + K steps + K read-backs are timed.
     h2d = NVECS * n * 8
     d2h = n * 8 + 8 * 24
+    XB = []
+    for v in vec["X"]:
+        c = P.Clone(v)
+        lib.N_VSetHostArrayPointer_B200(P.host(v, n).ctypes.data_as(C.POINTER(C.c_double)), c)  # shared pinned mirror
+        XB.append(c)
+    suites = [suite, Suite(perf, vec, X=XB)]
+    xsets = [vec["X"], XB]
 
-    def step_e2e():
-        for v in vec["X"]:
-            P.to_device(v)      # pinned host mirror -> HBM (cudaMemcpyAsync + sync)
-        step()
-        P.from_device(vec["Z"][1])
+    def upload(which):
+        for v in xsets[which]:
+            lib.N_VCopyToDeviceAsync_B200(v)
 
-    for _ in range(min(3, args.warmup)):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    def run_e2e(k):
+        upload(0)
+        lib.N_VCopyJoin_B200(vec["X"][0])
+        for i in range(k):
+            cur = i & 1
+            if i + 1 < k:
+                upload(1 - cur)
+            suites[cur].step(1)
+            P.from_device(vec["Z"][1])          # D2H of the step's result vector (+ the scalars already on the host)
+            lib.N_VCopyJoin_B200(vec["X"][0])    # the next step's inputs must have landed (stream-side wait)
+
+    run_e2e(min(3, args.warmup))
+    ms_e2e = timed(lambda: run_e2e(args.steps)) / args.steps
+    suites[1].check()
     clocks = sampler.stop() if rank == 0 else None
 
     value = world * bytes_per_step / (ms_step * 1e-3) / 1e9
     e2e_value = world * bytes_per_step / (ms_e2e * 1e-3) / 1e9
 
-    # ---- per-op timings: each op alone, CUDA events.  EVERY rank runs this loop --
-    # the reducing ops of a distributed vector are collectives (SPMD) -- rank 0 reports
+    # ---- per-op timings: each op alone in a C loop, CUDA events ("API": for a scalar-returning op the
+    # call blocks until the host has the value).  EVERY rank runs this loop -- the reducing ops of a
+    # distributed vector are collectives (SPMD) -- rank 0 reports
     per_op = {}
-    peaks = {}
-    pk = ROOT / "MEASURED_PEAKS.json"
-    if pk.exists():
-        peaks = json.loads(pk.read_text())
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     reps = 10
-    for name, bpe, fn in suite:
-        fn()
+    for i, name in enumerate(suite.names):
+        suite.op(i, 1)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(reps):
-            fn()
+        suite.op(i, reps)
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / reps * 1e3
-        per_op[name] = {"us": round(us, 2), "GBs": round(bpe * n / us / 1e3, 1),
-                        "frac_of_peak": round(bpe * n / us / 1e3 / peak, 3)}
+        per_op[name] = {"us": round(us, 2), "GBs": round(suite.bpe[i] * n / us / 1e3, 1),
+                        "frac_of_peak": round(suite.bpe[i] * n / us / 1e3 / peak, 3)}
 
-    # reductions: the API-level time above includes the host round trip that
-    # returning a scalar requires; also time the kernels alone (C ABI, async)
-    dptr = lib.N_VGetDeviceArrayPointer_B200
-    X, Y, Z = vec["X"], vec["Y"], vec["Z"]
-    W, ID, CN = vec["W"], vec["ID"], vec["CN"]
-
-    def tab(vs):
-        return (C.c_void_p * len(vs))(*[dptr(v) for v in vs])
-
-    tX, tY = tab(X), tab(Y)
-    kernel_only = {
-        "N_VDotProd": (16, lambda: lib.b200vec_dot_prod(ctx, dptr(X[1]), dptr(Y[1]), n, None)),
-        "N_VMaxNorm": (8, lambda: lib.b200vec_max_norm(ctx, dptr(X[2]), n, None)),
-        "N_VWrmsNorm": (16, lambda: lib.b200vec_wsqr_sum(ctx, dptr(X[3]), dptr(W), n, None)),
-        "N_VWrmsNormMask": (24, lambda: lib.b200vec_wsqr_sum_mask(ctx, dptr(X[4]), dptr(W), dptr(ID), n, None)),
-        "N_VMin": (8, lambda: lib.b200vec_min(ctx, dptr(X[5]), n, None)),
-        "N_VL1Norm": (8, lambda: lib.b200vec_l1_norm(ctx, dptr(X[7]), n, None)),
-        "N_VInvTest": (16, lambda: lib.b200vec_inv_test(ctx, dptr(X[1]), dptr(Z[1]), n, None)),
-        "N_VConstrMask": (24, lambda: lib.b200vec_constr_mask(ctx, dptr(CN), dptr(X[2]), dptr(Z[2]), n, None)),
-        "N_VMinQuotient": (16, lambda: lib.b200vec_min_quotient(ctx, dptr(X[3]), dptr(Y[3]), n, None)),
-        "N_VDotProdMulti": (8 * (NVECS + 1), lambda: lib.b200vec_dot_prod_multi(ctx, NVECS, dptr(X[2]), tY, n, None)),
-        "N_VWrmsNormVectorArray": (16 * NVECS,
-                                   lambda: lib.b200vec_wsqr_sum_vector_array(ctx, NVECS, tX, tY, None, n, None)),
-        "N_VWrmsNormMaskVectorArray": (8 * (2 * NVECS + 1),
-                                       lambda: lib.b200vec_wsqr_sum_vector_array(ctx, NVECS, tX, tY, dptr(ID), n, None)),
-    }
-    for name, (bpe, fn) in kernel_only.items():
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / reps * 1e3
-        per_op[name].update({"kernel_us": round(us, 2), "kernel_GBs": round(bpe * n / us / 1e3, 1),
-                             "kernel_frac_of_peak": round(bpe * n / us / 1e3 / peak, 3)})
+    # scalar-returning ops: where the API time goes.  dev_us = %globaltimer from the kernel's first CTA
+    # to the publication of the result (device side, one stamped call); the rest of the API time is the
+    # launch path + the PCIe hand-off + the host poll, which no kernel design removes.
+    lib.b200vec_ctx_set_tuning(ctx, b"profile", 1)
+    for i, name in enumerate(suite.names):
+        if not suite.scalar[i]:
+            continue
+        devs = []
+        for _ in range(3):
+            lib.b200vec_ctx_set_tuning(ctx, b"prof_stamp_reset", 1)
+            suite.op(i, 1)
+            t0 = lib.b200vec_ctx_get_tuning(ctx, b"prof_counter_6")
+            t1 = lib.b200vec_ctx_get_tuning(ctx, b"prof_counter_7")
+            if 0 < t0 < t1:
+                devs.append((t1 - t0) * 1e-3)
+        if devs:
+            d = sorted(devs)[len(devs) // 2]
+            per_op[name].update({"dev_us": round(d, 2), "dev_frac_of_peak": round(suite.bpe[i] * n / d / 1e3 / peak, 3),
+                                 "launch_and_return_us": round(per_op[name]["us"] - d, 2)})
+    lib.b200vec_ctx_set_tuning(ctx, b"profile", 0)
 
     # dominant kernel by share of the step (profiles/r01_launches_summary.md: 28 %):
     # k_scaleadd_rows<4>, launched 3x per step (N_VScaleAddMulti-1/-2, 136 B/elt, and
     # N_VScaleAddMultiVectorArray, 576 B/elt).  achieved = algorithmic bytes of
     # those launches / their CUDA-event time, measured live above.
     dom_ops = ["N_VScaleAddMulti-1", "N_VScaleAddMulti-2", "N_VScaleAddMultiVectorArray"]
-    dom_bytes = {name: bpe * n for name, bpe, _ in suite if name in dom_ops}
+    dom_bytes = {name: suite.bpe[suite.names.index(name)] * n for name in dom_ops}
     dom_us = sum(per_op[k]["us"] for k in dom_ops)
     dom_gbs = sum(dom_bytes.values()) / dom_us / 1e3
     roofline = {"bound": "hbm", "kernel": "k_scaleadd_rows<4> (N_VScaleAddMulti, N_VScaleAddMultiVectorArray)",
                 "achieved": round(dom_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(dom_gbs / peak, 4),
                 "traffic": None, "peak_source": peak_src,
                 "launches_per_step": 3,
-                "algorithmic_bytes_per_launch": {k: dom_bytes[k] for k in dom_ops},
+                "algorithmic_bytes_per_launch": dom_bytes,
                 "avg_launch_us": round(dom_us / 3, 2),
                 "share_of_step": round(dom_us / (ms_step * 1e3), 4),
                 "suite_frac": round(value / world / peak, 4)}
@@ -682,6 +951,19 @@ def b200_arm(args):
             roofline["traffic_launch"] = t.get("kernel")
         except Exception:
             pass
+
+    # the suite's vectors are no longer needed: the legs below allocate their own
+    for v in XB:
+        P.Destroy(v)
+    for v in all_handles(vec):
+        P.Destroy(v)
+    lib.b200vec_ctx_sync(ctx)
+
+    def leg_clock_min(d):
+        try:
+            return min(g["sm_mhz_min"] for g in d["clocks"].values())
+        except Exception:
+            return None
 
     # ---- ARKODE diffusion_2D solve time (second half of BASELINE's metric); collective
     diffusion = None
@@ -706,7 +988,7 @@ def b200_arm(args):
             ar3d["clocks"] = leg.stop(world)
 
     # ---- Krylov Gram-Schmidt built on the ops: the reference's unmodified
-    # SUNClassicalGS / SUNModifiedGS on a basis of this vector; collective
+    # SUNClassicalGS / SUNModifiedGS, and the fused SUNClassicalGS_B200, on a basis of this vector; collective
     gs = None
     if not args.no_gs:
         try:
@@ -715,16 +997,35 @@ def b200_arm(args):
 
             gs = gs_bench.run(args.log2n, maxl=5, reps=5, cpu_log2n=args.cpu_log2n, with_ref_cuda=False,
                               with_cpu=(world == 1 and not args.no_cpu_baseline), b200_ctx=ctx, rank=rank, world=world)
-            for k in ("classical", "modified"):
+            for k in gs["b200"]:
                 gs["b200"][k]["cycle_frac_of_peak"] = round(gs["b200"][k]["cycle_GBs"] / peak, 3)
         except Exception as e:
             gs = {"unavailable": f"{type(e).__name__}: {e}"}
+
+    # ---- length sweep (BASELINE config 3), bounded in the default run; collective
+    sweep = None
+    if not args.no_sweep:
+        try:
+            lengths = list(range(16, 31, 2)) if args.sweep else [16, 20, 24, 28]
+            cpu_lengths = [L for L in lengths if L <= 26] if args.sweep else [16, 20, 24]
+            sweep = run_sweep(P, lib, perf, ctx, world, rank, dist, torch, peak, lengths, cpu_lengths,
+                              with_cpu=(not args.no_cpu_baseline and (world == 1 or args.sweep)))
+        except Exception as e:
+            sweep = {"unavailable": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
         return 0
+
+    # ---- CVODE cvDiurnal_kry (BASELINE config 2), single GPU / host program
+    cvd = None
+    if not args.no_cvdiurnal:
+        try:
+            cvd = run_cvdiurnal()
+        except Exception as e:
+            cvd = {"unavailable": f"{type(e).__name__}: {e}"}
 
     if ar3d is not None and "solve_s" in ar3d and world == 1 and not args.no_cpu_baseline:
         try:
@@ -743,34 +1044,68 @@ def b200_arm(args):
     if world == 1 and not args.no_cpu_baseline:
         try:
             threads = os.cpu_count() or 1
-            g_omp, _, sample_omp, _ = run_reference_suite(args.cpu_log2n, 2, 1, threads, budget_s=25.0)
-            g_ser, _, sample_ser, _ = run_reference_suite(min(args.cpu_log2n, 20), 1, 0, 1, budget_s=15.0)
+            g_omp, _, sample_omp, _, chk = run_reference_suite(args.cpu_log2n, 2, 1, threads, budget_s=25.0)
+            g_ser, _, sample_ser, _, _ = run_reference_suite(min(args.cpu_log2n, 20), 1, 0, 1, budget_s=15.0)
             cpu = {"value": round(g_omp, 2), "unit": "GB/s", "cores": threads, "kind": "reference",
-                   "sample": sample_omp, "serial_1core_GBs": round(g_ser, 2), "serial_sample": sample_ser}
+                   "sample": sample_omp + " (bounded sample of the workload)", "serial_1core_GBs": round(g_ser, 2),
+                   "serial_sample": sample_ser}
         except Exception as e:  # the baseline is reported, never required
             cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "reference",
                    "sample": f"unavailable: {e}"}
 
-    cfg = workload_config(args)
+    # ---- compact record of the legs, printed LAST so that it survives any tail cut of the line
+    legs = {}
+    if parity is not None:
+        legs["dist_parity"] = {"ok": parity.get("ok"), "world": world, "transports": parity.get("transports")}
+    if diffusion and "solve_s" in diffusion:
+        legs["diffusion_2D"] = {"ms_per_ls_iter": diffusion["ms_per_ls_iter"], "ls_iters": diffusion["ls_iters"],
+                                "solve_s": diffusion["solve_s"], "sm_mhz_min": leg_clock_min(diffusion)}
+    if ar3d and "solve_s" in ar3d:
+        legs["advection_reaction_3D"] = {"solve_s": ar3d["solve_s"], "steps": ar3d["steps"], "fe": ar3d["fe_evals"],
+                                         "nni": ar3d["nls_iters"], "nli": ar3d["ls_iters"],
+                                         "sm_mhz_min": leg_clock_min(ar3d)}
+    if gs and "b200" in gs:
+        legs["gram_schmidt"] = {k: gs["b200"][k]["cycle_frac_of_peak"] for k in gs["b200"]}
+    if cvd and "b200_pinned_s" in cvd:
+        legs["cvDiurnal_kry"] = {"b200_s": cvd["b200_pinned_s"], "serial_s": cvd.get("serial_1core_s"),
+                                 "identical": cvd.get("stdout_identical_to_serial_golden")}
+    if sweep and "lengths" in sweep:
+        sw = {"ge0.8_of_9": sweep.get("classes_ge_0.8_of_peak")}
+        for L in ("2^16", "2^20"):
+            try:
+                sw[f"dot_us_{L}"] = sweep["lengths"][L]["ops"]["N_VDotProd"]["us"]
+            except KeyError:
+                pass
+        legs["sweep"] = sw
+    red = ["N_VDotProd", "N_VMaxNorm", "N_VMin", "N_VL1Norm", "N_VWrmsNorm", "N_VWrmsNormMask", "N_VInvTest",
+           "N_VConstrMask", "N_VMinQuotient"]
+    legs["reductions_api_frac"] = {k[3:]: per_op[k]["frac_of_peak"] for k in red}
+    legs["reductions_dev_frac"] = {k[3:]: per_op[k].get("dev_frac_of_peak") for k in red}
+
     lib.b200vec_comm_transport.restype = C.c_char_p
-    cfg["reduction_transport"] = lib.b200vec_comm_transport(ctx).decode()
     line = {
         "metric": "N_Vector op suite throughput (algorithmic GB/s)", "value": round(value, 1), "unit": "GB/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": cfg,
+        "config": workload_config(args),
         "e2e": {"value": round(e2e_value, 1), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": round(ms_e2e, 4)},
+                "ms_per_step": round(ms_e2e, 4),
+                "overlap": "uploads double-buffered on the context's copy stream (N_VCopyToDeviceAsync_B200)"},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
+        "reduction_transport": lib.b200vec_comm_transport(ctx).decode(),
+        "result_checksum": result_value,
+        "ops_per_step": suite.nops,
+        "dist_parity": parity,
         "diffusion_2D": diffusion,
         "advection_reaction_3D": ar3d,
         "gram_schmidt": gs,
+        "cvDiurnal_kry": cvd,
+        "sweep": sweep,
         "per_op": per_op,
-        "result_checksum": result_value,
-        "ops_per_step": len(suite),
+        "legs": legs,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -796,9 +1131,15 @@ def main():
     ap.add_argument("--ar3d-npts", type=int, default=512, help="GLOBAL mesh points per direction")
     ap.add_argument("--ar3d-tf", type=float, default=0.05)
     ap.add_argument("--no-gs", action="store_true", help="skip the Gram-Schmidt leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the (bounded) length sweep leg")
+    ap.add_argument("--sweep", action="store_true", help="full length sweep 2^16 .. 2^30 with CPU columns up to 2^26")
+    ap.add_argument("--no-cvdiurnal", action="store_true", help="skip the CVODE cvDiurnal_kry leg")
+    ap.add_argument("--only-suite", action="store_true", help="op suite only: skip every leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.only_suite:
+        args.no_diffusion = args.no_ar3d = args.no_gs = args.no_sweep = args.no_cvdiurnal = True
     if args.impl == "reference":
         return reference_arm(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -254,7 +254,7 @@ void next_xargs(b200vec_ctx ctx, XArgs* x) { fill_xargs(ctx, x); }
 /* standalone exchange of result slots [0,count) (count <= kMaxOut): warp j folds
    slot j across ranks in place */
 template <int OP>
-__global__ void __launch_bounds__(kBlock) k_xrank(double* d_res, int count, XArgs x)
+__global__ void __launch_bounds__(kBlock) k_xrank(double* d_res, int count, const __grid_constant__ XArgs x)
 {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -143,15 +143,27 @@ __device__ __forceinline__ double xrank_combine_warp(double v, int slot, const X
   double vq                    = C::identity();
   unsigned long long prof_t0   = 0;
   if (x.prof && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_t0));
+  /* mailbox of peer `lane` and the own one, picked by compile-time indices: a run-time index into
+     the by-value XArgs would make the compiler copy the whole struct into LOCAL memory at the top of
+     every kernel that can reach this function (an 88-byte stack frame per thread: ~13 MB of stores
+     for a 296 x 512 grid, 3-4 us on a 20 us reduction -- measured, profiles/r02_reduce_attribution.md) */
+  unsigned long long* mb_peer = nullptr;
+  unsigned long long* mb_own  = nullptr;
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; r++)
+  {
+    if (lane == r) mb_peer = x.mbox[r];
+    if (x.rank == r) mb_own = x.mbox[r];
+  }
   if (lane < x.nranks)
   {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-    unsigned long long* dst = x.mbox[lane] + ((size_t)(par * kMaxPeers + x.rank) * kMaxOut + slot) * 2;
+    unsigned long long* dst = mb_peer + ((size_t)(par * kMaxPeers + x.rank) * kMaxOut + slot) * 2;
     const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(w0) : "memory");
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(w1) : "memory");
 
-    const unsigned long long* src = x.mbox[x.rank] + ((size_t)(par * kMaxPeers + lane) * kMaxOut + slot) * 2;
+    const unsigned long long* src = mb_own + ((size_t)(par * kMaxPeers + lane) * kMaxOut + slot) * 2;
     unsigned long long a, b, t0 = 0;
     unsigned int spins = 0;
     for (;;)

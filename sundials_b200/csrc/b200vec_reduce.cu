@@ -306,7 +306,7 @@ __device__ __forceinline__ void prefetch_tile_l2(const RedPtrs& p, int64_t tile)
 
 template <int W, int U, class R>
 __global__ void __launch_bounds__(kRBlock, 2)
-  k_reduce(R r, RedPtrs p, int64_t n, unsigned long long* tagged, ResOut o, XArgs x, int pf)
+  k_reduce(R r, RedPtrs p, int64_t n, unsigned long long* tagged, ResOut o, const __grid_constant__ XArgs x, int pf)
 {
   using C = typename R::Comb;
   __shared__ double smem[kRBlock / 32];
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(kRBlock, 2)
 /* exact-order path: one CTA, terms staged in shared memory, thread 0 folds
    them left-to-right exactly as the serial loop does */
 template <class R>
-__global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, ResOut o, XArgs x)
+__global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, ResOut o, const __grid_constant__ XArgs x)
 {
   using C = typename R::Comb;
   __shared__ double buf[kExactMaxElems];
@@ -600,6 +600,7 @@ __device__ __forceinline__ void multi_combine_and_publish(double* s_fin, int nou
     __syncthreads();
   }
   if (threadIdx.x < nout) publish_slot(o, threadIdx.x, s_fin[threadIdx.x]);
+  if (x.prof && threadIdx.x == 0) x.prof[7] = global_ns();
 }
 
 /* NO = outputs compiled in (2, 4, 8, 16 or 24; the launch's nout <= NO), U = tiles in flight per
@@ -612,7 +613,7 @@ __device__ __forceinline__ void multi_combine_and_publish(double* s_fin, int nou
    while the shared operand's tile stays in registers: x is still read once for all of them. */
 template <int W, int MODE, int NO, int U>
 __global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__ MultiArgs m, int64_t n,
-                                                         double* partials, unsigned int* counter, ResOut o, XArgs x)
+                                                         double* partials, unsigned int* counter, ResOut o, const __grid_constant__ XArgs x)
 {
   static_assert(NO <= kMaxOut && (MODE == 0 || NO <= kMaxPair), "outputs per launch");
   constexpr int NB = (NO < 8) ? NO : 8; /* operands whose loads are in flight together */
@@ -629,6 +630,7 @@ __global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__
 #pragma unroll
   for (int j = 0; j < NO; j++) acc[j] = 0.0;
   pdl_prologue();
+  if (x.prof && threadIdx.x == 0) atomicMin(x.prof + 6, global_ns());
 
   for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
   {
@@ -744,7 +746,7 @@ __global__ void __launch_bounds__(kBlock) k_reduce_multi(const __grid_constant__
 /* exact-order multi: n * nout <= kExactMaxElems; thread j folds column j */
 template <int MODE>
 __global__ void __launch_bounds__(kBlock)
-  k_reduce_multi_exact(const __grid_constant__ MultiArgs m, int n, ResOut o, XArgs x)
+  k_reduce_multi_exact(const __grid_constant__ MultiArgs m, int n, ResOut o, const __grid_constant__ XArgs x)
 {
   __shared__ double buf[kExactMaxElems];
   __shared__ double s_fin[kMaxOut];
@@ -930,7 +932,7 @@ struct LcNormArgs
 
 template <int W>
 __global__ void __launch_bounds__(kBlock)
-  k_lincomb_sqnorm(const __grid_constant__ LcNormArgs a, int64_t n, unsigned long long* tagged, ResOut o, XArgs x)
+  k_lincomb_sqnorm(const __grid_constant__ LcNormArgs a, int64_t n, unsigned long long* tagged, ResOut o, const __grid_constant__ XArgs x)
 {
   __shared__ double s_c[kLcnMaxTerms];
   __shared__ const double* s_x[kLcnMaxTerms];
@@ -998,7 +1000,7 @@ __global__ void __launch_bounds__(kBlock)
 
 /* exact-order form (n <= exact_threshold): z as above, then thread 0 adds z_0^2, z_1^2, ...
    strictly left to right -- the bits of serial's N_VLinearCombination + N_VDotProd */
-__global__ void __launch_bounds__(kBlock) k_lincomb_sqnorm_exact(const __grid_constant__ LcNormArgs a, int n, ResOut o, XArgs x)
+__global__ void __launch_bounds__(kBlock) k_lincomb_sqnorm_exact(const __grid_constant__ LcNormArgs a, int n, ResOut o, const __grid_constant__ XArgs x)
 {
   __shared__ double buf[kExactMaxElems];
   pdl_prologue();

@@ -24,13 +24,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = Path(__file__).resolve().parent.parent
-BIN = ROOT / "oracle" / "_ref" / "bin"
+BIN = ROOT / "oracle" / "_ref" / "bin"      # programs that contain the reference's CPU vectors
+BINB = ROOT / "baseline" / "_ref" / "bin"   # reference programs on NVECTOR_B200 + the host framework only
 GOLD = ROOT / "tests" / "golden" / "examples"
 MANIFEST = json.loads((GOLD / "MANIFEST.json").read_text())
 
 
 def _run(exe, *args, timeout=600):
-    p = BIN / exe
+    p = (BINB if (BINB / exe).exists() else BIN) / exe
     assert p.exists(), f"{p} missing: run `make -C tests/c` where /root/reference exists"
     return subprocess.run([str(p), *map(str, args)], capture_output=True, text=True, timeout=timeout)
 
@@ -82,7 +83,7 @@ def test_spgmr_uses_the_fused_gs_by_symbol_interposition():
     so = ROOT / "sundials_b200" / "lib" / "libsundials_b200gs.so"
     assert so.exists()
     env = dict(os.environ, LD_PRELOAD=str(so), B200GS_REPORT="1")
-    p = BIN / "test_sunlinsol_spgmr_b200"
+    p = BINB / "test_sunlinsol_spgmr_b200"
     # args of the reference CTest (spgmr/serial/CMakeLists.txt:35): n, gstype (2 = classical), pretype, maxl, tol, timing
     r = subprocess.run([str(p), "100", "2", "1", "100", "1e-13", "0"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,6 +1,6 @@
 """Gram-Schmidt orthogonalisation on the new vector: the reference's
-UNMODIFIED SUNClassicalGS / SUNModifiedGS (src/sundials/sundials_iterative.c:45-170, from
-libsundials_ref.so) building a Krylov basis column by column exactly as SPGMR does
+UNMODIFIED SUNClassicalGS / SUNModifiedGS (src/sundials/sundials_iterative.c:45-170, from the
+host framework baseline/_ref/lib/libsundials_host.so), plus the fused SUNClassicalGS_B200, building a Krylov basis column by column exactly as SPGMR does
 (sunlinsol_spgmr.c: orthogonalise v[k] against v[0..k-1], normalise by the returned norm),
 timed per call on
 
@@ -36,6 +36,8 @@ dp = C.POINTER(C.c_double)
 
 
 def ideal_bytes(gs, k, n):
+    if gs == "fused_classical":   # multi-dot 8N(k+1) + in-place combination with the norm in its epilogue 8N(k+2)
+        return 8 * n * (2 * k + 3)
     return 8 * n * (2 * k + 4) if gs == "classical" else 8 * n * (5 * k + 2)
 
 
@@ -49,7 +51,7 @@ def bind_core(core):
     core.N_VDestroy.restype, core.N_VDestroy.argtypes = None, [V]
 
 
-def time_gs(core, newvec, fill, sync, n, maxl, reps):
+def time_gs(core, newvec, fill, sync, n, maxl, reps, fused=None):
     """Returns {gs: {"per_k_us": [...], "cycle_us": total of k = 1..maxl, "h_last": ...}}.
     S[k]: fixed pseudo-random source columns; V[k]: the basis being built."""
     S = [newvec() for _ in range(maxl + 1)]
@@ -63,7 +65,7 @@ def time_gs(core, newvec, fill, sync, n, maxl, reps):
     h = (dp * (maxl + 1))(*[C.cast(r, dp) for r in rows])
     nrm = C.c_double()
     out = {}
-    for gs in ("classical", "modified"):
+    for gs in ("classical", "modified") + (("fused_classical",) if fused is not None else ()):
         per_k = {k: [] for k in range(1, maxl + 1)}
         for rep in range(reps + 1):                      # first pass = warm-up
             core.N_VScale(1.0, S[0], Vv[0])
@@ -75,6 +77,8 @@ def time_gs(core, newvec, fill, sync, n, maxl, reps):
                 t0 = time.perf_counter()
                 if gs == "classical":
                     rc = core.SUNClassicalGS(basis, h, k, maxl, C.byref(nrm), stemp, vtemp)
+                elif gs == "fused_classical":
+                    rc = fused(basis, h, k, maxl, C.byref(nrm), stemp, vtemp)
                 else:
                     rc = core.SUNModifiedGS(basis, h, k, maxl, C.byref(nrm))
                 dt = time.perf_counter() - t0
@@ -90,6 +94,8 @@ def time_gs(core, newvec, fill, sync, n, maxl, reps):
             "per_k_GBs": [round(ideal_bytes(gs, k, n) / med[k - 1] / 1e3, 1) for k in range(1, maxl + 1)],
             "cycle_us": round(sum(med), 2),
             "cycle_GBs": round(sum(ideal_bytes(gs, k, n) for k in range(1, maxl + 1)) / sum(med) / 1e3, 1),
+            "cycle_GBs_at_unfused_traffic": round(sum(ideal_bytes("classical" if "classical" in gs else gs, k, n)
+                                                      for k in range(1, maxl + 1)) / sum(med) / 1e3, 1),
             "h_last_column": [rows[i][maxl - 1] for i in range(maxl)],
             "last_norm": nrm.value,
             "max_abs_dot_with_last": orth,
@@ -118,7 +124,9 @@ def run(log2n=24, maxl=5, reps=5, cpu_log2n=22, with_ref_cuda=True, with_cpu=Tru
     from sundials_b200.plugin import B200Plugin
 
     n = 1 << log2n
-    core = bench.load_reference()
+    # NVECTOR_B200 needs only the unmodified host framework (baseline/_ref); the reference's CPU / CUDA
+    # vectors (oracle/_ref) are loaded further down, for the baselines alone
+    core = bench.load_host()
     bind_core(core)
     sctx = C.c_void_p()
     assert core.SUNContext_Create(0, C.byref(sctx)) == 0
@@ -148,11 +156,16 @@ def run(log2n=24, maxl=5, reps=5, cpu_log2n=22, with_ref_cuda=True, with_cpu=Tru
         P.to_device(v)
         P.drop_host(v)
 
-    res["b200"] = time_gs(core, new_b200, fill_b200, torch.cuda.synchronize, n, maxl, reps)
+    lib.SUNClassicalGS_B200.restype = C.c_int
+    lib.SUNClassicalGS_B200.argtypes = [C.POINTER(V), C.POINTER(dp), C.c_int, C.c_int, dp, dp, C.POINTER(V)]
+    res["b200"] = time_gs(core, new_b200, fill_b200, torch.cuda.synchronize, n, maxl, reps, fused=lib.SUNClassicalGS_B200)
+    res["ideal_bytes"] += "; fused_classical (SUNClassicalGS_B200: 2 kernels per column) 8N(2k+3)"
 
     # ---- reference nvector_cuda on the same GPU
     so = ROOT / "oracle" / "_ref" / "lib" / "libsundials_nveccuda_ref.so"
     if with_ref_cuda and world == 1 and so.exists():
+        core = bench.load_reference()
+        bind_core(core)
         cu = C.CDLL(str(so), mode=C.RTLD_GLOBAL)
         cu.N_VNew_Cuda.restype, cu.N_VNew_Cuda.argtypes = V, [C.c_int64, V]
         cu.N_VEnableFusedOps_Cuda.restype, cu.N_VEnableFusedOps_Cuda.argtypes = C.c_int, [V, C.c_int]
@@ -177,6 +190,8 @@ def run(log2n=24, maxl=5, reps=5, cpu_log2n=22, with_ref_cuda=True, with_cpu=Tru
 
     # ---- nvector_openmp on the host cores, bounded length
     if with_cpu and world == 1:
+        core = bench.load_reference()
+        bind_core(core)
         threads = os.cpu_count() or 1
         nc = 1 << min(cpu_log2n, log2n)
 

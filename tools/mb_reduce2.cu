@@ -168,10 +168,15 @@ __device__ __forceinline__ void finish(double v /* thread 0 */, const Out& o, do
 
 // PART 0: tiles round-robin over CTAs; 1: one contiguous tile range per CTA.
 // PIPE 1: next tile's loads are issued before the current tile is folded.
-template <int BLOCK, int MINB, int U, int NIN, int PART, int PIPE, int FIN>
+template <int BLOCK, int MINB, int U, int NIN, int PART, int PIPE, int FIN, int PDL = 0>
 __global__ void __launch_bounds__(BLOCK, MINB) k_red(const double* x, const double* y, const double* z, int64_t n, Out o)
 {
   __shared__ double smem[BLOCK / 32];
+  if (PDL)
+  {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   constexpr int W        = 4;
   constexpr int64_t TILE = (int64_t)BLOCK * W * U;
   constexpr int64_t STEP = (int64_t)BLOCK * W;
@@ -478,6 +483,31 @@ static void run(Bench& B, int cap)
   });
 }
 
+// PDL 1: griddepcontrol in the kernel, plain launch.  2: + programmatic-stream-serialization launch attribute
+template <int BLOCK, int MINB, int U, int NIN, int FIN, int PDL>
+static void run_pdl(Bench& B, int cap)
+{
+  const int64_t tiles = std::max<int64_t>(1, B.n / ((int64_t)BLOCK * 4 * U));
+  const int grid      = (int)std::min<int64_t>(tiles, cap);
+  const int nb        = (int)B.bufs.size();
+  char name[128];
+  snprintf(name, sizeof(name), "ldg B=%d minb=%d U=%d NIN=%d fin=%d PDL=%d%s", BLOCK, MINB, U, NIN, FIN, PDL,
+           PDL == 2 ? " (+launch attr)" : PDL == 1 ? " (griddepcontrol only)" : "");
+  measure(B, name, grid, FIN, 8.0 * NIN * B.n, [&](int r) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = dim3(grid);
+    cfg.blockDim           = dim3(BLOCK);
+    cfg.stream             = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                        = at;
+    cfg.numAttrs                                     = (PDL == 2) ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, k_red<BLOCK, MINB, U, NIN, 0, 0, FIN, (PDL > 0)>, (const double*)B.bufs[(3 * r) % nb],
+                          (const double*)B.bufs[(3 * r + 1) % nb], (const double*)B.bufs[(3 * r + 2) % nb], B.n, B.o));
+  });
+}
+
 template <int CW, int STAGES, int CHUNK, int NIN, int FIN>
 static void run_tma(Bench& B, int cap)
 {
@@ -500,6 +530,17 @@ static void sweep(Bench& B)
 {
   const int S = 148;
   printf("---- NIN=%d  n=2^%d\n", NIN, (int)__builtin_ctzll((unsigned long long)B.n));
+  // launch path: plain <<<>>> vs cudaLaunchKernelEx, griddepcontrol, PDL launch attribute
+  run_pdl<512, 2, 4, NIN, 2, 0>(B, 2 * S);
+  run_pdl<512, 2, 4, NIN, 2, 1>(B, 2 * S);
+  run_pdl<512, 2, 4, NIN, 2, 2>(B, 2 * S);
+  // same buffers every launch (what a per-op timing loop does) instead of rotating over 3 GiB
+  {
+    std::vector<double*> keep = B.bufs;
+    B.bufs.resize(3);
+    run<512, 2, 4, NIN, 0, 0, 2>(B, 2 * S);
+    B.bufs = keep;
+  }
   // round-1 product shape and its epilogue variants
   run<512, 2, 4, NIN, 0, 0, 0>(B, 2 * S);
   run<512, 2, 4, NIN, 0, 0, 1>(B, 2 * S);
