@@ -30,13 +30,15 @@
 
 namespace b200 {
 
-constexpr int kLcMaxTerms = 16;
+constexpr int kLcMaxTerms = 32; /* GMRES with maxl = 20 updates the solution with a 21-term combination
+                                   (sunlinsol_spgmr.c:790,866): one launch, z written once */
 constexpr int kLcMaxRows  = 16;
+constexpr int kLcMaxPtrs  = 256; /* terms x rows per launch: the parameter struct stays under 4 KB */
 constexpr int kTermBatch  = 4; /* loads of this many terms are in flight together */
 
 struct LinCombArgs
 {
-  const double* X[kLcMaxTerms * kLcMaxRows]; /* X[i * nrows + r] */
+  const double* X[kLcMaxPtrs]; /* X[i * nrows + r] */
   double* Z[kLcMaxRows];
   double c[kLcMaxTerms];
   int nterms;
@@ -276,9 +278,13 @@ static int lincomb_rows(b200vec_ctx ctx, int nterms, int nrows, const double* c,
 {
   if (n == 0) return B200VEC_OK;
   DeviceGuard g(ctx->device);
-  for (int r0 = 0; r0 < nrows; r0 += kLcMaxRows)
+  /* rows per launch: as many as the pointer table holds for this term count */
+  const int nt_launch = (nterms < kLcMaxTerms) ? nterms : kLcMaxTerms;
+  int rows_per        = kLcMaxPtrs / nt_launch;
+  if (rows_per > kLcMaxRows) rows_per = kLcMaxRows;
+  for (int r0 = 0; r0 < nrows; r0 += rows_per)
   {
-    const int nr = (nrows - r0 < kLcMaxRows) ? nrows - r0 : kLcMaxRows;
+    const int nr = (nrows - r0 < rows_per) ? nrows - r0 : rows_per;
     int i0       = 0;
     bool first   = true;
     while (i0 < nterms)

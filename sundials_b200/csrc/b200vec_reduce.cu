@@ -537,6 +537,14 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
       c.grid = (int)((tiles < ctx->tune.max_blocks) ? tiles : ctx->tune.max_blocks);
     }
     c.grid = min(c.grid, reduce_grid_cap(ctx, n));
+    if (R::HAS_OUT && ctx->tune.max_blocks == kMaxBlocksDef && n > ((int64_t)1 << 20))
+    { /* InvTest / ConstrMask also WRITE a vector: like the streaming kernels they run best with one
+         tile per CTA (the block scheduler back-fills SMs as CTAs retire; measured 48.2 -> see
+         profiles/r02_reduce_attribution.md); CTA 0 then polls up to kMaxPartialBlocks slots */
+      int64_t tiles = n / ((int64_t)kRBlock * c.W * c.U);
+      if (tiles < 1) tiles = 1;
+      c.grid = (int)((tiles < kMaxPartialBlocks) ? tiles : kMaxPartialBlocks);
+    }
 #define B200_RED_CASE(WW, UU)    \
   if (c.W == WW && c.U == UU)    \
   launch_k(ctx, k_reduce<WW, UU, R>, dim3(c.grid), dim3(kRBlock), r, p, n, ctx->d_tagged, out, xa, \

@@ -348,3 +348,26 @@ def test_min_returns_a_nan_at_x0_like_serial(be, oracle):
         x[0] = np.nan
         got, want = nv.N_VMin(nv.N_VMake(torch.from_numpy(x).cuda(), be.ctx)), oracle.min(x)
         assert np.isnan(got) and np.isnan(want)
+
+
+@pytest.mark.parametrize("nvec", [17, 21, 32, 33, 40])
+def test_wide_linear_combination_one_launch_up_to_32_terms(be, oracle, nvec):
+    """GMRES with maxl = 20 updates the solution with a 21-term combination (sunlinsol_spgmr.c:790):
+    bit-exact against the oracle, one launch up to 32 terms, z carried through beyond"""
+    from sundials_b200 import nvector as nv
+
+    n = 70_001
+    rng = np.random.default_rng(nvec)
+    X = [rng.uniform(-1, 1, n) for _ in range(nvec)]
+    c = [float(v) for v in rng.uniform(-1, 1, nvec)]
+    for inplace in (False, True):
+        Xo = [a.copy() for a in X]
+        dX = [nv.N_VMake(torch.from_numpy(a.copy()).cuda(), be.ctx) for a in X]
+        zo, dz = (Xo[0], dX[0]) if inplace else (np.empty(n), nv.N_VNew(n, be.ctx))
+        be.ctx.set_tuning("count_launches", 1)
+        nv.N_VLinearCombination(c, dX, dz)
+        launches = be.ctx.launch_count()
+        be.ctx.set_tuning("count_launches", 0)
+        oracle.linear_combination(c, Xo, zo)
+        assert np.array_equal(_bits(dz.data.cpu().numpy()), _bits(zo)), (nvec, inplace)
+        assert launches == (1 if nvec <= 32 else 2), launches

@@ -215,12 +215,13 @@ def main():
     ap.add_argument("--maxl", type=int, default=5, help="Krylov dimension (SPGMR default 5)")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cpu-log2n", type=int, default=22)
+    ap.add_argument("--no-baselines", action="store_true", help="NVECTOR_B200 only (e.g. under ncu)")
     a = ap.parse_args()
     import torch
 
     torch.cuda.set_device(0)
     torch.cuda.init()
-    out = run(a.log2n, a.maxl, a.reps, a.cpu_log2n)
+    out = run(a.log2n, a.maxl, a.reps, a.cpu_log2n, with_ref_cuda=not a.no_baselines, with_cpu=not a.no_baselines)
     out["gpu"] = torch.cuda.get_device_name(0)
     print(json.dumps(out))
 

@@ -1,6 +1,6 @@
 """Launch each representative kernel a few times (target for ncu captures).
    ncu --set full --clock-control none --import-source on -k regex:'k_map|k_reduce|k_lincomb|k_scaleadd' \
-       -c 40 -o gpurun_out/prof python tools/profile_kernels.py --n 24"""
+       -s 11 -c 11 -o gpurun_out/prof python tools/profile_kernels.py --n 24   (second repetition)"""
 import argparse
 import sys
 from pathlib import Path
@@ -28,5 +28,7 @@ for _ in range(a.reps):
     nv.N_VScaleAddMulti(c, V[10], V[:8], V[11:19])           # k_scaleadd_rows<4>
     nv.N_VDotProdMulti(V[19], V[:8])                         # k_reduce_multi<4,0>
     nv.N_VWrmsNormVectorArray(V[:8], V[11:19])               # k_reduce_multi<4,1>
+    nv.N_VLinearCombinationSqNorm([1.0] + c[:5], [V[20]] + V[:5], V[20])   # k_lincomb_sqnorm<4> (fused CGS step, k = 5)
+    nv.N_VDotProdMulti(V[21], V[:20] + [V[21]])              # k_reduce_multi<4,0,24,1>: 21-wide (GMRES maxl = 20)
 torch.cuda.synchronize()
 print("done")
