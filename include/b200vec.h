@@ -156,6 +156,12 @@ int b200vec_constr_mask(b200vec_ctx ctx, const double* c, const double* x, doubl
 int b200vec_min_quotient(b200vec_ctx ctx, const double* num, const double* denom, int64_t n,
                          double* result_host);
 
+/* z <- a x + z (serial's Vaxpy form, serial:1734) and result = sum_i w_i z_i of the UPDATED z, one
+ * pass: a modified Gram-Schmidt step -- N_VLinearSum(1, v_k, -h_i, v_i, v_k) + N_VDotProd(v_{i+1}, v_k),
+ * src/sundials/sundials_iterative.c:62-67 -- at 32 B/elt instead of 24 + 16.  w may alias x. */
+int b200vec_axpy_dot(b200vec_ctx ctx, double a, const double* x, double* z, const double* w, int64_t n,
+                     double* result_host);
+
 /* device-resident result slots of the last reduction(s): slot k of the context */
 double* b200vec_result_device(b200vec_ctx ctx);
 /* sync the stream and copy `count` slots to host (after b200vec_allreduce) */

@@ -130,6 +130,9 @@ SUNErrCode N_VDotProdMulti_B200(int nvec, N_Vector x, N_Vector* Y, sunrealtype* 
 /* not an ops-table slot: z = sum c_i X_i and *sqnorm = z . z in ONE pass (used by
  * SUNClassicalGS_B200, include/sundials_iterative_b200.h) */
 SUNErrCode N_VLinearCombinationSqNorm_B200(int nvec, sunrealtype* c, N_Vector* X, N_Vector z, sunrealtype* sqnorm);
+/* not an ops-table slot: z <- a x + z and *dot = w . z of the updated z in ONE pass (used by
+ * SUNModifiedGS_B200) */
+SUNErrCode N_VAxpyDot_B200(sunrealtype a, N_Vector x, N_Vector z, N_Vector w, sunrealtype* dot);
 
 SUNErrCode N_VLinearSumVectorArray_B200(int nvec, sunrealtype a, N_Vector* X, sunrealtype b, N_Vector* Y,
                                         N_Vector* Z);

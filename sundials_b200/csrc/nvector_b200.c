@@ -774,6 +774,17 @@ SUNErrCode N_VLinearCombinationSqNorm_B200(int nvec, sunrealtype* c, N_Vector* X
   return map_err(rc);
 }
 
+/* z <- a x + z and *dot = w . z(updated) (GLOBAL on a distributed vector): N_VLinearSum(1, z, a, x, z)
+   + N_VDotProd(w, z) of a modified Gram-Schmidt sweep (sundials_iterative.c:62-67) in one kernel */
+SUNErrCode N_VAxpyDot_B200(sunrealtype a, N_Vector x, N_Vector z, N_Vector w, sunrealtype* dot)
+{
+  if (!dot) return SUN_ERR_ARG_OUTOFRANGE;
+  int rc = NDIST(z) ? b200vec_ctx_set_scope(NCTX(z), B200VEC_SCOPE_GLOBAL) : B200VEC_OK;
+  if (!rc) rc = b200vec_axpy_dot(NCTX(z), a, NDEV(x), NDEV(z), NDEV(w), NLEN(z), dot);
+  if (!rc) coherent_sync(z);
+  return map_err(rc);
+}
+
 SUNErrCode N_VScaleAddMulti_B200(int nvec, sunrealtype* a, N_Vector x, N_Vector* Y, N_Vector* Z)
 {
   if (nvec < 1) return SUN_ERR_ARG_OUTOFRANGE;

@@ -61,3 +61,68 @@ SUNErrCode SUNClassicalGS_B200(N_Vector* v, sunrealtype** h, int k, int p, sunre
   }
   return SUN_SUCCESS;
 }
+
+/* ------------------------------------------------------------------ modified Gram-Schmidt
+ * ref:45-105.  Every N_VLinearSum of the sweep is fused with the N_VDotProd that follows it. */
+static long g_mgs_calls = 0;
+long SUNModifiedGS_B200_Calls(void) { return g_mgs_calls; }
+
+SUNErrCode SUNModifiedGS_B200(N_Vector* v, sunrealtype** h, int k, int p, sunrealtype* new_vk_norm)
+{
+  const int k_minus_1 = k - 1;
+  const int i0        = (k - p > 0) ? k - p : 0; /* ref:56 */
+  SUNErrCode err;
+  sunrealtype d2[2], hi, sq = 0.0;
+  g_mgs_calls++;
+  if (i0 >= k)
+  { /* nothing to orthogonalise against (k == 0): the reference computes the norm twice */
+    *new_vk_norm = rsqrt_guard(N_VDotProd_B200(v[k], v[k]));
+    return SUN_SUCCESS;
+  }
+
+  /* ||v_k||^2 and the first projection in one 2-wide multi-dot (ref:52 + first pass of ref:62) */
+  N_Vector y2[2] = {v[k], v[i0]};
+  err = N_VDotProdMulti_B200(2, v[k], y2, d2);
+  if (err) return err;
+  const sunrealtype vk_norm = rsqrt_guard(d2[0]);
+  hi                        = d2[1];
+
+  for (int i = i0; i < k; i++) /* ref:60-66 */
+  {
+    h[i][k_minus_1] = hi;
+    if (i + 1 < k)
+    { /* v_k <- v_k - h_i v_i, and h_{i+1} = v_{i+1} . v_k on the updated vector */
+      err = N_VAxpyDot_B200(-hi, v[i], v[k], v[i + 1], &hi);
+      if (err) return err;
+    }
+    else
+    { /* last update together with the new norm (ref:70) */
+      sunrealtype c2[2] = {1.0, -hi};
+      N_Vector x2[2]    = {v[k], v[i]};
+      err               = N_VLinearCombinationSqNorm_B200(2, c2, x2, v[k], &sq);
+      if (err) return err;
+    }
+  }
+  *new_vk_norm = rsqrt_guard(sq);
+
+  /* ref:79-80: reorthogonalise only if the new vector is tiny against the old one */
+  sunrealtype temp = FACTOR * vk_norm;
+  if ((temp + (*new_vk_norm)) != temp) return SUN_SUCCESS;
+
+  sunrealtype new_norm_2 = 0.0; /* ref:82-102, rare: the unfused ops */
+  for (int i = i0; i < k; i++)
+  {
+    sunrealtype new_product = N_VDotProd_B200(v[i], v[k]);
+    temp                    = FACTOR * h[i][k_minus_1];
+    if ((temp + new_product) == temp) continue;
+    h[i][k_minus_1] += new_product;
+    N_VLinearSum_B200(1.0, v[k], -new_product, v[i], v[k]);
+    new_norm_2 += new_product * new_product;
+  }
+  if (new_norm_2 != 0.0)
+  {
+    sunrealtype new_product = (*new_vk_norm) * (*new_vk_norm) - new_norm_2;
+    *new_vk_norm            = (new_product > 0.0) ? rsqrt_guard(new_product) : 0.0;
+  }
+  return SUN_SUCCESS;
+}

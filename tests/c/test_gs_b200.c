@@ -9,8 +9,9 @@
  *
  *   test_gs_b200 <n> <maxl> <tol>      tol = 0 demands bit-identical results
  *
- * A third pass compares the reference's SUNClassicalGS on nvector_serial with the fused
- * SUNClassicalGS_B200 (include/sundials_iterative_b200.h) on NVECTOR_B200.
+ * A third and a fourth pass compare the reference's SUNClassicalGS / SUNModifiedGS on nvector_serial
+ * with the fused SUNClassicalGS_B200 / SUNModifiedGS_B200 (include/sundials_iterative_b200.h) on
+ * NVECTOR_B200.
  * Prints one line per (gstype, k) and exits with the number of mismatches.
  */
 #include <math.h>
@@ -26,9 +27,10 @@
 #include "sundials_iterative_b200.h"
 
 #define FUSED_CLASSICAL_GS 3 /* serial: reference SUNClassicalGS; B200: SUNClassicalGS_B200 (2 kernels per column) */
+#define FUSED_MODIFIED_GS  4 /* serial: reference SUNModifiedGS;  B200: SUNModifiedGS_B200 (k + 1 kernels per column) */
 static const char* gsname(int t)
 {
-  return t == SUN_MODIFIED_GS ? "modified " : t == SUN_CLASSICAL_GS ? "classical" : "fused-cgs";
+  return t == SUN_MODIFIED_GS ? "modified " : t == SUN_CLASSICAL_GS ? "classical" : t == FUSED_CLASSICAL_GS ? "fused-cgs" : "fused-mgs";
 }
 
 static void fill(sunrealtype* d, sunindextype n, unsigned seed)
@@ -56,7 +58,7 @@ int main(int argc, char** argv)
   if (SUNContext_Create(SUN_COMM_NULL, &ctx)) return 99;
   int bad = 0;
 
-  for (int gstype = SUN_MODIFIED_GS; gstype <= FUSED_CLASSICAL_GS; gstype++)
+  for (int gstype = SUN_MODIFIED_GS; gstype <= FUSED_MODIFIED_GS; gstype++)
   {
     N_Vector ts = N_VNew_Serial(n, ctx);
     N_Vector tb = N_VNew_B200(n, ctx);
@@ -97,10 +99,15 @@ int main(int argc, char** argv)
         SUNClassicalGS(Vs, Hs, k, maxl, &nrm_s, ss, ws);
         SUNClassicalGS(Vb, Hb, k, maxl, &nrm_b, sb, wb);
       }
-      else
+      else if (gstype == FUSED_CLASSICAL_GS)
       {
         SUNClassicalGS(Vs, Hs, k, maxl, &nrm_s, ss, ws);
         SUNClassicalGS_B200(Vb, Hb, k, maxl, &nrm_b, sb, wb);
+      }
+      else
+      {
+        SUNModifiedGS(Vs, Hs, k, maxl, &nrm_s);
+        SUNModifiedGS_B200(Vb, Hb, k, maxl, &nrm_b);
       }
       int kb = differ(nrm_s, nrm_b, tol, nrm_s);
       double hmax = 0;

@@ -371,3 +371,28 @@ def test_wide_linear_combination_one_launch_up_to_32_terms(be, oracle, nvec):
         oracle.linear_combination(c, Xo, zo)
         assert np.array_equal(_bits(dz.data.cpu().numpy()), _bits(zo)), (nvec, inplace)
         assert launches == (1 if nvec <= 32 else 2), launches
+
+
+@pytest.mark.parametrize("n", [7, 1000, 1025, 300_001, (1 << 21) + 17])
+def test_axpy_dot_matches_linear_sum_then_dot_prod(be, oracle, n):
+    """the fused modified-Gram-Schmidt step: z bit-identical to N_VLinearSum(1, z, a, x, z), the dot equal
+    to N_VDotProd(w, z) on the updated z (bitwise on the exact path)"""
+    import ctypes as C
+
+    from sundials_b200 import nvector as nv
+    from sundials_b200._lib import check
+
+    rng = np.random.default_rng(n % 1009)
+    for a in (-0.37, 1.0, -1.0):
+        x, z, w = (rng.uniform(-1, 1, n) for _ in range(3))
+        dx, dz, dw = (nv.N_VMake(torch.from_numpy(v.copy()).cuda(), be.ctx) for v in (x, z, w))
+        r = C.c_double()
+        check(be.ctx.lib.b200vec_axpy_dot(be.ctx.h, a, dx.ptr, dz.ptr, dw.ptr, n, C.byref(r)), "axpy_dot")
+        zo = z.copy()
+        oracle.linear_sum(1.0, zo, a, x, zo)
+        want = oracle.dot_prod(w, zo)
+        assert np.array_equal(_bits(dz.data.cpu().numpy()), _bits(zo)), a
+        if n <= 1024:
+            assert r.value == want, (a, r.value, want)
+        else:
+            assert abs(r.value - want) <= RTOL * float(np.abs(w * zo).sum()), (a, r.value, want)

@@ -65,34 +65,41 @@ def test_gram_schmidt_tolerance_large():
     assert "SUCCESS" in r.stdout
 
 
-def test_fused_classical_gs_matches_reference_cgs_on_serial():
-    """third pass of test_gs_b200: SUNClassicalGS_B200 (2 kernels per column) on NVECTOR_B200 against the
-    reference's SUNClassicalGS on nvector_serial -- bit-identical at n = 1000, 1e-13 at 300 000"""
+def test_fused_gs_matches_reference_gs_on_serial():
+    """third / fourth pass of test_gs_b200: SUNClassicalGS_B200 (2 kernels per column) and SUNModifiedGS_B200
+    (k + 1 kernels per column) on NVECTOR_B200 against the reference's SUNClassicalGS / SUNModifiedGS on
+    nvector_serial -- bit-identical at n = 1000, 1e-13 at 300 000"""
     r = _run("test_gs_b200", 1000, 10, 0)
-    assert r.returncode == 0 and r.stdout.count("fused-cgs k=") == 10 and "MISMATCH" not in r.stdout, r.stdout
+    assert r.returncode == 0 and "MISMATCH" not in r.stdout, r.stdout
+    assert r.stdout.count("fused-cgs k=") == 10 and r.stdout.count("fused-mgs k=") == 10, r.stdout
     r = _run("test_gs_b200", 300_000, 20, 1e-13)
-    assert r.returncode == 0 and r.stdout.count("fused-cgs k=") == 20 and "MISMATCH" not in r.stdout, r.stdout
+    assert r.returncode == 0 and "MISMATCH" not in r.stdout, r.stdout
+    assert r.stdout.count("fused-cgs k=") == 20 and r.stdout.count("fused-mgs k=") == 20, r.stdout
 
 
-def test_spgmr_uses_the_fused_gs_by_symbol_interposition():
-    """the reference's UNMODIFIED SPGMR unit test (classical Gram-Schmidt, gstype 2) with
-    libsundials_b200gs.so preloaded: its SUNClassicalGS calls land in SUNClassicalGS_B200
-    (interposed, reference unmodified) and the 1e-13 solve still passes"""
+@pytest.mark.parametrize("prog", ["test_sunlinsol_spgmr_b200", "test_sunlinsol_spfgmr_b200"])
+@pytest.mark.parametrize("gstype,routine", [(1, "SUNModifiedGS_B200"), (2, "SUNClassicalGS_B200")])
+def test_krylov_solvers_use_the_fused_gs_by_symbol_interposition(prog, gstype, routine):
+    """the reference's UNMODIFIED SPGMR / SPFGMR unit tests (both Gram-Schmidt types) with
+    libsundials_b200gs.so preloaded: their SUNModifiedGS / SUNClassicalGS calls land in the fused _B200
+    routines (interposed, reference unmodified) and the 1e-13 solves still pass, printing the same text"""
     import os
 
     so = ROOT / "sundials_b200" / "lib" / "libsundials_b200gs.so"
     assert so.exists()
     env = dict(os.environ, LD_PRELOAD=str(so), B200GS_REPORT="1")
-    p = BINB / "test_sunlinsol_spgmr_b200"
-    # args of the reference CTest (spgmr/serial/CMakeLists.txt:35): n, gstype (2 = classical), pretype, maxl, tol, timing
-    r = subprocess.run([str(p), "100", "2", "1", "100", "1e-13", "0"], capture_output=True, text=True, timeout=600, env=env)
+    p = BINB / prog
+    # args of the reference CTests (spgmr/serial/CMakeLists.txt:34-37: n, gstype, pretype, maxl, tol, timing;
+    # spfgmr/serial/CMakeLists.txt:34-35: n, gstype, maxl, tol, timing)
+    args = [str(p), "100", str(gstype)] + (["1"] if "spgmr" in prog else []) + ["100", "1e-13", "0"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "FAIL" not in r.stdout
-    calls = [int(x.rsplit(":", 1)[1]) for x in r.stderr.splitlines() if "SUNClassicalGS_B200 calls" in x]
+    calls = [int(x.rsplit(":", 1)[1]) for x in r.stderr.splitlines() if f"{routine} calls" in x]
     assert calls and calls[0] > 0, r.stderr[-500:]
-    # and without the preload the same program never reaches it
-    r0 = subprocess.run([str(p), "100", "2", "1", "100", "1e-13", "0"], capture_output=True, text=True, timeout=600)
-    assert r0.returncode == 0 and r0.stdout == r.stdout  # same printed solve, fused or not
+    # and without the preload the same program never reaches it, and prints the same solve
+    r0 = subprocess.run(args, capture_output=True, text=True, timeout=600)
+    assert r0.returncode == 0 and r0.stdout == r.stdout
 
 
 def test_reference_cuda_example_with_device_rhs_kernels():

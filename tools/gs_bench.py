@@ -38,6 +38,8 @@ dp = C.POINTER(C.c_double)
 def ideal_bytes(gs, k, n):
     if gs == "fused_classical":   # multi-dot 8N(k+1) + in-place combination with the norm in its epilogue 8N(k+2)
         return 8 * n * (2 * k + 3)
+    if gs == "fused_modified":    # 2-wide multi-dot 16N + (k-1) x axpy+dot 32N + last update with the norm 24N
+        return 8 * n * (4 * k + 1)
     return 8 * n * (2 * k + 4) if gs == "classical" else 8 * n * (5 * k + 2)
 
 
@@ -65,7 +67,7 @@ def time_gs(core, newvec, fill, sync, n, maxl, reps, fused=None):
     h = (dp * (maxl + 1))(*[C.cast(r, dp) for r in rows])
     nrm = C.c_double()
     out = {}
-    for gs in ("classical", "modified") + (("fused_classical",) if fused is not None else ()):
+    for gs in ("classical", "modified") + (("fused_classical", "fused_modified") if fused is not None else ()):
         per_k = {k: [] for k in range(1, maxl + 1)}
         for rep in range(reps + 1):                      # first pass = warm-up
             core.N_VScale(1.0, S[0], Vv[0])
@@ -78,7 +80,9 @@ def time_gs(core, newvec, fill, sync, n, maxl, reps, fused=None):
                 if gs == "classical":
                     rc = core.SUNClassicalGS(basis, h, k, maxl, C.byref(nrm), stemp, vtemp)
                 elif gs == "fused_classical":
-                    rc = fused(basis, h, k, maxl, C.byref(nrm), stemp, vtemp)
+                    rc = fused[0](basis, h, k, maxl, C.byref(nrm), stemp, vtemp)
+                elif gs == "fused_modified":
+                    rc = fused[1](basis, h, k, maxl, C.byref(nrm))
                 else:
                     rc = core.SUNModifiedGS(basis, h, k, maxl, C.byref(nrm))
                 dt = time.perf_counter() - t0
@@ -94,7 +98,7 @@ def time_gs(core, newvec, fill, sync, n, maxl, reps, fused=None):
             "per_k_GBs": [round(ideal_bytes(gs, k, n) / med[k - 1] / 1e3, 1) for k in range(1, maxl + 1)],
             "cycle_us": round(sum(med), 2),
             "cycle_GBs": round(sum(ideal_bytes(gs, k, n) for k in range(1, maxl + 1)) / sum(med) / 1e3, 1),
-            "cycle_GBs_at_unfused_traffic": round(sum(ideal_bytes("classical" if "classical" in gs else gs, k, n)
+            "cycle_GBs_at_unfused_traffic": round(sum(ideal_bytes(gs.replace("fused_", ""), k, n)
                                                       for k in range(1, maxl + 1)) / sum(med) / 1e3, 1),
             "h_last_column": [rows[i][maxl - 1] for i in range(maxl)],
             "last_norm": nrm.value,
@@ -158,8 +162,12 @@ def run(log2n=24, maxl=5, reps=5, cpu_log2n=22, with_ref_cuda=True, with_cpu=Tru
 
     lib.SUNClassicalGS_B200.restype = C.c_int
     lib.SUNClassicalGS_B200.argtypes = [C.POINTER(V), C.POINTER(dp), C.c_int, C.c_int, dp, dp, C.POINTER(V)]
-    res["b200"] = time_gs(core, new_b200, fill_b200, torch.cuda.synchronize, n, maxl, reps, fused=lib.SUNClassicalGS_B200)
-    res["ideal_bytes"] += "; fused_classical (SUNClassicalGS_B200: 2 kernels per column) 8N(2k+3)"
+    lib.SUNModifiedGS_B200.restype = C.c_int
+    lib.SUNModifiedGS_B200.argtypes = [C.POINTER(V), C.POINTER(dp), C.c_int, C.c_int, dp]
+    res["b200"] = time_gs(core, new_b200, fill_b200, torch.cuda.synchronize, n, maxl, reps,
+                          fused=(lib.SUNClassicalGS_B200, lib.SUNModifiedGS_B200))
+    res["ideal_bytes"] += ("; fused_classical (SUNClassicalGS_B200: 2 kernels per column) 8N(2k+3); fused_modified "
+                           "(SUNModifiedGS_B200: k + 1 kernels per column) 8N(4k+1)")
 
     # ---- reference nvector_cuda on the same GPU
     so = ROOT / "oracle" / "_ref" / "lib" / "libsundials_nveccuda_ref.so"
