@@ -162,6 +162,19 @@ int b200vec_min_quotient(b200vec_ctx ctx, const double* num, const double* denom
 int b200vec_axpy_dot(b200vec_ctx ctx, double a, const double* x, double* z, const double* w, int64_t n,
                      double* result_host);
 
+/* ---- chained Gram-Schmidt sweeps: all kernels of one orthogonalisation column launched back to back,
+ * each reading the coefficient(s) it needs from the DEVICE result slots its predecessor wrote, ONE host
+ * wait per column (src/sundials/sundials_iterative.c:45-80 and :130-146; see sundials_iterative_b200.h).
+ * V / Ydots / Xcomb: HOST arrays of DEVICE pointers. */
+/* modified: res = {v_k.v_k, h_0..h_{nproj-1}, ||v_k||^2 after}; v_k <- v_k - sum h_i V_i, every h_i taken on
+ * the vector updated so far.  nproj + 1 kernels. */
+int b200vec_mgs_sweep(b200vec_ctx ctx, int nproj, double* vk, const double* const* V, int64_t n,
+                      double* h_host, double* norms_host /* [2] */);
+/* classical: dots_j = x . Ydots_j (j < nvec <= 24);  z <- Xcomb_0 - sum_{j>=1} dots_{j-1} Xcomb_j and
+ * *sqnorm_host = z . z.  2 kernels. */
+int b200vec_cgs_step(b200vec_ctx ctx, int nvec, const double* x, const double* const* Ydots,
+                     const double* const* Xcomb, double* z, int64_t n, double* dots_host, double* sqnorm_host);
+
 /* device-resident result slots of the last reduction(s): slot k of the context */
 double* b200vec_result_device(b200vec_ctx ctx);
 /* sync the stream and copy `count` slots to host (after b200vec_allreduce) */

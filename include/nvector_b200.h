@@ -133,6 +133,11 @@ SUNErrCode N_VLinearCombinationSqNorm_B200(int nvec, sunrealtype* c, N_Vector* X
 /* not an ops-table slot: z <- a x + z and *dot = w . z of the updated z in ONE pass (used by
  * SUNModifiedGS_B200) */
 SUNErrCode N_VAxpyDot_B200(sunrealtype a, N_Vector x, N_Vector z, N_Vector w, sunrealtype* dot);
+/* whole Gram-Schmidt columns as ONE chain of kernels with one host wait (coefficients stay on the device
+ * between the kernels): h[nproj], norms[2] = {vk.vk before, after}; dots[nvec], *sqnorm */
+SUNErrCode N_VModifiedGSSweep_B200(int nproj, N_Vector* V, N_Vector vk, sunrealtype* h, sunrealtype* norms);
+SUNErrCode N_VClassicalGSStep_B200(int nvec, N_Vector x, N_Vector* Ydots, N_Vector* Xcomb, N_Vector z,
+                                   sunrealtype* dots, sunrealtype* sqnorm);
 
 SUNErrCode N_VLinearSumVectorArray_B200(int nvec, sunrealtype a, N_Vector* X, sunrealtype b, N_Vector* Y,
                                         N_Vector* Z);

@@ -79,6 +79,8 @@ _SIGS = {
     "b200vec_constr_mask": (_I, [ctx_t, _V, _V, _V, _L, c_double_p]),
     "b200vec_min_quotient": (_I, [ctx_t, _V, _V, _L, c_double_p]),
     "b200vec_axpy_dot": (_I, [ctx_t, _D, _V, _V, _V, _L, c_double_p]),
+    "b200vec_mgs_sweep": (_I, [ctx_t, _I, _V, c_ptr_table, _L, c_double_p, c_double_p]),
+    "b200vec_cgs_step": (_I, [ctx_t, _I, _V, c_ptr_table, c_ptr_table, _V, _L, c_double_p, c_double_p]),
     "b200vec_result_device": (_V, [ctx_t]),
     "b200vec_result_fetch": (_I, [ctx_t, _I, c_double_p]),
     "b200vec_linear_combination": (_I, [ctx_t, _I, c_double_p, c_ptr_table, _V, _L]),

@@ -170,6 +170,9 @@ struct RAxpyDot
   static constexpr bool NAN_HEAD = false;
   static constexpr int MAXU = 2;
   double a;
+  const double* a_dev; /* NULL, or: a = -(*a_dev), read on the device when the kernel starts -- the
+                          projection a preceding kernel of the same sweep left in a result slot, so the
+                          host need not see it before launching this kernel */
   __device__ double term(double x, double z, double w, double& outv, bool& store) const
   {
     store = true;
@@ -177,6 +180,16 @@ struct RAxpyDot
     return w * outv;
   }
 };
+
+/* hook run by every reduction kernel after griddepcontrol.wait: policies with device-resident
+   parameters load them here (the kernel's by-value copy of the policy is thread-private) */
+template <class R>
+__device__ __forceinline__ void prepare_policy(R&)
+{}
+__device__ __forceinline__ void prepare_policy(RAxpyDot& r)
+{
+  if (r.a_dev) r.a = -__ldcg(r.a_dev);
+}
 
 struct RedPtrs
 {
@@ -196,7 +209,10 @@ struct ResOut
 {
   double* d_res;
   unsigned long long* h_words; /* words of slot 0 of this launch, or NULL: no host publication */
-  unsigned int tag;            /* low 32 bits of the context's reduction sequence number       */
+  unsigned int tag;            /* low 32 bits of the context's reduction sequence number: tags the
+                                  CTA partials of THIS launch                                     */
+  unsigned int htag;           /* tag of the pinned words: == tag, except inside a chained sweep
+                                  (several kernels, one host wait) where all launches share one    */
 };
 
 __device__ __forceinline__ void store_tagged(unsigned long long* dst, unsigned int tag, double v)
@@ -210,7 +226,7 @@ __device__ __forceinline__ void store_tagged(unsigned long long* dst, unsigned i
 __device__ __forceinline__ void publish_slot(const ResOut& o, int slot, double v)
 {
   o.d_res[slot] = v;
-  if (o.h_words) store_tagged(o.h_words + 2 * slot, o.tag, v);
+  if (o.h_words) store_tagged(o.h_words + 2 * slot, o.htag, v);
 }
 
 /* ticket of the last-block-done scheme (multi-output kernels): ONE acq_rel atomic releases this
@@ -334,6 +350,7 @@ __global__ void __launch_bounds__(kRBlock, 2)
   constexpr int64_t STEP = (int64_t)kRBlock * W;
   const int64_t nfull    = n / TILE;
   pdl_prologue();
+  prepare_policy(r);
   if (x.prof && threadIdx.x == 0) atomicMin(x.prof + 6, global_ns());
   if (W < 2) pf = 0; /* bulk prefetch needs 16-byte aligned addresses */
 
@@ -418,6 +435,7 @@ __global__ void __launch_bounds__(kBlock) k_reduce_exact(R r, RedPtrs p, int n, 
   using C = typename R::Comb;
   __shared__ double buf[kExactMaxElems];
   pdl_prologue();
+  prepare_policy(r);
   if (x.prof && threadIdx.x == 0) atomicMin(x.prof + 6, global_ns());
   for (int i = threadIdx.x; i < n; i += kBlock)
   {
@@ -447,6 +465,7 @@ static ResOut next_out(b200vec_ctx ctx, int slot0, bool to_host)
   o.d_res   = ctx->d_result + slot0;
   o.h_words = to_host ? (unsigned long long*)(ctx->h_result_dev + kMaxRows) + 2 * slot0 : nullptr;
   o.tag     = (unsigned int)ctx->seq;
+  o.htag    = o.tag;
   return o;
 }
 
@@ -454,11 +473,11 @@ static ResOut next_out(b200vec_ctx ctx, int slot0, bool to_host)
    last, then decode them.  The final pass stores them straight into pinned host memory: polling
    costs ~1 us after the kernel's last store, a cudaStreamSynchronize round trip several times that.
    Bounded spin, then fall back to the sync (which also surfaces asynchronous errors). */
-static int finish_host(b200vec_ctx ctx, int slot0, int count, double* result_host)
+static int finish_host(b200vec_ctx ctx, int slot0, int count, double* result_host, long long want_tag = -1)
 {
   if (!result_host) return B200VEC_OK;
   volatile unsigned long long* w = (volatile unsigned long long*)(ctx->h_result + kMaxRows) + 2 * slot0;
-  const unsigned int want        = (unsigned int)ctx->seq;
+  const unsigned int want        = (want_tag < 0) ? (unsigned int)ctx->seq : (unsigned int)want_tag;
   bool seen                      = false;
   if (ctx->tune.spin_wait)
   {
@@ -515,6 +534,54 @@ static int reduce_grid_cap(b200vec_ctx ctx, int64_t n)
   return (int)cap;
 }
 
+/* launch ONE single-output reduction kernel for policy R (exact-order or tree form), result into
+   slot `slot0`; no host wait */
+template <class R>
+static int launch_reduce_kernel(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int64_t n, const ResOut& out,
+                                const XArgs& xa)
+{
+  if (n <= ctx->tune.exact_threshold) { launch_k(ctx, k_reduce_exact<R>, dim3(1), dim3(kBlock), r, p, (int)n, out, xa); }
+  else
+  {
+    int wmax = align_width(p.p0);
+    wmax     = min(wmax, align_width(p.p1));
+    wmax     = min(wmax, align_width(p.p2));
+    wmax     = min(wmax, align_width(p.out));
+    MapCfg c = pick_map_cfg(ctx, n, wmax, true, kRBlock);
+    if (c.U > R::MAXU)
+    { /* keep the instantiation within 64 registers (2 CTAs x 512 threads per SM) */
+      c.U           = R::MAXU;
+      int64_t tiles = n / ((int64_t)kRBlock * c.W * c.U);
+      if (tiles < 1) tiles = 1;
+      c.grid = (int)((tiles < ctx->tune.max_blocks) ? tiles : ctx->tune.max_blocks);
+    }
+    c.grid = min(c.grid, reduce_grid_cap(ctx, n));
+    if (R::HAS_OUT && ctx->tune.max_blocks == kMaxBlocksDef && n > ((int64_t)1 << 20))
+    { /* InvTest / ConstrMask / AxpyDot also WRITE a vector: like the streaming kernels they run best
+         with one tile per CTA (the block scheduler back-fills SMs as CTAs retire; InvTest 48.2 -> 42.4 us
+         at 2^24, profiles/r02_reduce_attribution.md); CTA 0 then polls up to kMaxPartialBlocks slots */
+      int64_t tiles = n / ((int64_t)kRBlock * c.W * c.U);
+      if (tiles < 1) tiles = 1;
+      c.grid = (int)((tiles < kMaxPartialBlocks) ? tiles : kMaxPartialBlocks);
+    }
+#define B200_RED_CASE(WW, UU)    \
+  if (c.W == WW && c.U == UU)    \
+  launch_k(ctx, k_reduce<WW, UU, R>, dim3(c.grid), dim3(kRBlock), r, p, n, ctx->d_tagged, out, xa, \
+           (int)ctx->tune.l2_prefetch)
+    B200_RED_CASE(4, 4);
+    else B200_RED_CASE(4, 2);
+    else B200_RED_CASE(4, 1);
+    else B200_RED_CASE(2, 4);
+    else B200_RED_CASE(2, 2);
+    else B200_RED_CASE(2, 1);
+    else B200_RED_CASE(1, 4);
+    else B200_RED_CASE(1, 2);
+    else B200_RED_CASE(1, 1);
+#undef B200_RED_CASE
+  }
+  return check_launch(ctx, name);
+}
+
 template <class R>
 static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int64_t n, double empty_value,
                          double* result_host)
@@ -541,46 +608,7 @@ static int launch_reduce(b200vec_ctx ctx, const char* name, R r, RedPtrs p, int6
      kernel with n == 0 contributes the identity */
   const bool to_host = (result_host != nullptr) && scope != 2;
   const ResOut out   = next_out(ctx, 0, to_host);
-  if (n <= ctx->tune.exact_threshold) { launch_k(ctx, k_reduce_exact<R>, dim3(1), dim3(kBlock), r, p, (int)n, out, xa); }
-  else
-  {
-    int wmax = align_width(p.p0);
-    wmax     = min(wmax, align_width(p.p1));
-    wmax     = min(wmax, align_width(p.p2));
-    wmax     = min(wmax, align_width(p.out));
-    MapCfg c = pick_map_cfg(ctx, n, wmax, true, kRBlock);
-    if (c.U > R::MAXU)
-    { /* keep the instantiation within 64 registers (2 CTAs x 512 threads per SM) */
-      c.U           = R::MAXU;
-      int64_t tiles = n / ((int64_t)kRBlock * c.W * c.U);
-      if (tiles < 1) tiles = 1;
-      c.grid = (int)((tiles < ctx->tune.max_blocks) ? tiles : ctx->tune.max_blocks);
-    }
-    c.grid = min(c.grid, reduce_grid_cap(ctx, n));
-    if (R::HAS_OUT && ctx->tune.max_blocks == kMaxBlocksDef && n > ((int64_t)1 << 20))
-    { /* InvTest / ConstrMask also WRITE a vector: like the streaming kernels they run best with one
-         tile per CTA (the block scheduler back-fills SMs as CTAs retire; measured 48.2 -> see
-         profiles/r02_reduce_attribution.md); CTA 0 then polls up to kMaxPartialBlocks slots */
-      int64_t tiles = n / ((int64_t)kRBlock * c.W * c.U);
-      if (tiles < 1) tiles = 1;
-      c.grid = (int)((tiles < kMaxPartialBlocks) ? tiles : kMaxPartialBlocks);
-    }
-#define B200_RED_CASE(WW, UU)    \
-  if (c.W == WW && c.U == UU)    \
-  launch_k(ctx, k_reduce<WW, UU, R>, dim3(c.grid), dim3(kRBlock), r, p, n, ctx->d_tagged, out, xa, \
-           (int)ctx->tune.l2_prefetch)
-    B200_RED_CASE(4, 4);
-    else B200_RED_CASE(4, 2);
-    else B200_RED_CASE(4, 1);
-    else B200_RED_CASE(2, 4);
-    else B200_RED_CASE(2, 2);
-    else B200_RED_CASE(2, 1);
-    else B200_RED_CASE(1, 4);
-    else B200_RED_CASE(1, 2);
-    else B200_RED_CASE(1, 1);
-#undef B200_RED_CASE
-  }
-  int rc = check_launch(ctx, name);
+  int rc             = launch_reduce_kernel(ctx, name, r, p, n, out, xa);
   if (rc) return rc;
   if (scope == 2) return finish_global_nccl(ctx, 1, C::op, result_host);
   return finish_host(ctx, 0, 1, result_host);
@@ -836,9 +864,10 @@ static int launch_multi_cfg(b200vec_ctx ctx, const char* name, const MultiArgs& 
 
 template <int MODE>
 static int launch_multi_group(b200vec_ctx ctx, const char* name, const MultiArgs& m, int64_t n, int slot0,
-                              bool to_host, const XArgs& xa)
+                              bool to_host, const XArgs& xa, long long htag = -1)
 {
-  const ResOut out = next_out(ctx, slot0, to_host);
+  ResOut out = next_out(ctx, slot0, to_host);
+  if (htag >= 0) out.htag = (unsigned int)htag;
   if (n <= ctx->tune.exact_threshold && n * m.nout <= kExactMaxElems)
   {
     launch_k(ctx, k_reduce_multi_exact<MODE>, dim3(1), dim3(kBlock), m, (int)n, out, xa);
@@ -954,6 +983,9 @@ struct LcNormArgs
 {
   const double* X[kLcnMaxTerms];
   double c[kLcnMaxTerms];
+  const double* c_dev; /* NULL, or device-resident coefficients: c_0 = 1, c_j = -c_dev[j-1] (the projections
+                          a preceding multi-dot left in the result slots: classical Gram-Schmidt's
+                          stemp[i+1] = -stemp[i], sundials_iterative.c:135) */
   double* z;
   int nterms;
 };
@@ -966,12 +998,10 @@ __global__ void __launch_bounds__(kBlock)
   __shared__ const double* s_x[kLcnMaxTerms];
   __shared__ double smem[kBlock / 32];
   const int nterms = a.nterms;
+  if (threadIdx.x < nterms) s_x[threadIdx.x] = a.X[threadIdx.x];
+  pdl_prologue(); /* device-resident coefficients are valid only after the wait */
   if (threadIdx.x < nterms)
-  {
-    s_c[threadIdx.x] = a.c[threadIdx.x];
-    s_x[threadIdx.x] = a.X[threadIdx.x];
-  }
-  pdl_prologue();
+    s_c[threadIdx.x] = a.c_dev ? (threadIdx.x == 0 ? 1.0 : -__ldcg(a.c_dev + threadIdx.x - 1)) : a.c[threadIdx.x];
   if (x.prof && threadIdx.x == 0) atomicMin(x.prof + 6, global_ns());
   __syncthreads();
   double* z = a.z;
@@ -1031,11 +1061,15 @@ __global__ void __launch_bounds__(kBlock)
 __global__ void __launch_bounds__(kBlock) k_lincomb_sqnorm_exact(const __grid_constant__ LcNormArgs a, int n, ResOut o, const __grid_constant__ XArgs x)
 {
   __shared__ double buf[kExactMaxElems];
+  __shared__ double s_c[kLcnMaxTerms];
   pdl_prologue();
+  if (threadIdx.x < a.nterms)
+    s_c[threadIdx.x] = a.c_dev ? (threadIdx.x == 0 ? 1.0 : -__ldcg(a.c_dev + threadIdx.x - 1)) : a.c[threadIdx.x];
+  __syncthreads();
   for (int i = threadIdx.x; i < n; i += kBlock)
   {
-    double acc = a.c[0] * a.X[0][i];
-    for (int k = 1; k < a.nterms; k++) acc += a.c[k] * a.X[k][i];
+    double acc = s_c[0] * a.X[0][i];
+    for (int k = 1; k < a.nterms; k++) acc += s_c[k] * a.X[k][i];
     a.z[i] = acc;
     buf[i] = acc * acc;
   }
@@ -1048,6 +1082,89 @@ __global__ void __launch_bounds__(kBlock) k_lincomb_sqnorm_exact(const __grid_co
   }
   combine_and_publish<CombSum>(s, o, x);
 }
+
+/* launch k_lincomb_sqnorm (exact-order or tree form); c_dev != NULL: device-resident coefficients */
+static void launch_lincomb_sqnorm(b200vec_ctx ctx, int nvec, const double* c, const double* c_dev, const double* const* X,
+                                  double* z, int64_t n, const ResOut& out, const XArgs& xa)
+{
+  LcNormArgs a;
+  int wmax = align_width(z);
+  for (int i = 0; i < nvec; i++)
+  {
+    a.X[i] = X[i];
+    a.c[i] = c ? c[i] : 0.0;
+    wmax   = min(wmax, align_width(X[i]));
+  }
+  a.c_dev  = c_dev;
+  a.z      = z;
+  a.nterms = nvec;
+  if (n <= ctx->tune.exact_threshold) launch_k(ctx, k_lincomb_sqnorm_exact, dim3(1), dim3(kBlock), a, (int)n, out, xa);
+  else
+  {
+    int W = wmax;
+    if (ctx->tune.vec_width > 0 && ctx->tune.vec_width < W) W = (int)ctx->tune.vec_width;
+    int64_t tiles = n / ((int64_t)kBlock * W);
+    if (tiles < 1) tiles = 1;
+    int64_t cap = (int64_t)kSMs * 4; /* 4 CTAs of 256 threads per SM (64 registers): one resident wave */
+    if (ctx->tune.max_blocks != kMaxBlocksDef && cap > ctx->tune.max_blocks) cap = ctx->tune.max_blocks;
+    const int grid = (int)((tiles < cap) ? tiles : cap);
+    if (W == 4) launch_k(ctx, k_lincomb_sqnorm<4>, dim3(grid), dim3(kBlock), a, n, ctx->d_tagged, out, xa);
+    else if (W == 2) launch_k(ctx, k_lincomb_sqnorm<2>, dim3(grid), dim3(kBlock), a, n, ctx->d_tagged, out, xa);
+    else launch_k(ctx, k_lincomb_sqnorm<1>, dim3(grid), dim3(kBlock), a, n, ctx->d_tagged, out, xa);
+  }
+}
+
+/* ------------------------------------------------------------------ chained Gram-Schmidt sweeps
+ * All kernels of one orthogonalisation column are launched back to back: each one reads the
+ * coefficient(s) it needs from the DEVICE result slot(s) its predecessor wrote (stream order +
+ * griddepcontrol.wait make them visible), so the host does not sit between two kernels.  Every
+ * kernel publishes its scalar(s) to its own pinned slot under ONE shared host tag; the host waits
+ * once, at the end, for all of them.  One host round trip per column instead of k + 1 (modified) or
+ * 2 (classical), and programmatic dependent launch overlaps each kernel's launch ramp with its
+ * predecessor's tail. */
+struct Chain
+{
+  b200vec_ctx ctx;
+  int scope;          /* 0 local, 1 peer-memory exchange inside each kernel, 2 ncclAllReduce after each kernel */
+  XArgs xa;
+  bool first = true;
+  long long htag = -1;
+  bool to_host;
+
+  Chain(b200vec_ctx c, bool want_host) : ctx(c)
+  {
+    scope   = take_scope(c, &xa);
+    to_host = want_host && scope != 2;
+  }
+  /* bookkeeping before ANY launch of the chain; returns the chain's host tag (the sequence number of
+     its first launch).  For launchers that take their own sequence number (the multi-dot groups). */
+  long long advance()
+  {
+    if (!first && scope == 1) next_xargs(ctx, &xa); /* every kernel is its own collective */
+    if (first) htag = (long long)(unsigned int)(ctx->seq + 1);
+    first = false;
+    return htag;
+  }
+  /* ResOut of the next kernel of the chain: own partial tag, shared host tag, result in `slot` */
+  ResOut next(int slot)
+  {
+    const long long t = advance();
+    ResOut out        = next_out(ctx, slot, to_host);
+    out.htag          = (unsigned int)t;
+    return out;
+  }
+  /* NCCL transport: fold the slots the kernel just wrote before the next kernel reads them */
+  int after(int slot, int count)
+  {
+    if (scope != 2) return B200VEC_OK;
+    return b200vec_allreduce_buffer(ctx, ctx->d_result + slot, count, B200VEC_SUM);
+  }
+  int finish(int count, double* res)
+  {
+    if (scope == 2) return b200vec_result_fetch(ctx, count, res);
+    return finish_host(ctx, 0, count, res, htag);
+  }
+};
 
 } // namespace b200
 
@@ -1126,7 +1243,7 @@ int b200vec_axpy_dot(b200vec_ctx ctx, double a, const double* x, double* z, cons
                      double* result_host)
 {
   B200_RARGS(x && z && w);
-  return launch_reduce(ctx, "axpy_dot", RAxpyDot{a}, RedPtrs{x, z, w, z}, n, 0.0, result_host);
+  return launch_reduce(ctx, "axpy_dot", RAxpyDot{a, nullptr}, RedPtrs{x, z, w, z}, n, 0.0, result_host);
 }
 
 int b200vec_dot_prod_multi(b200vec_ctx ctx, int nvec, const double* x, const double* const* Y, int64_t n,
@@ -1197,36 +1314,140 @@ int b200vec_linear_combination_sqnorm(b200vec_ctx ctx, int nvec, const double* c
     if (result_host) *result_host = 0.0;
     return B200VEC_OK;
   }
-  LcNormArgs a;
-  int wmax = align_width(z);
-  for (int i = 0; i < nvec; i++)
-  {
-    a.X[i] = X[i];
-    a.c[i] = c[i];
-    wmax   = min(wmax, align_width(X[i]));
-  }
-  a.z      = z;
-  a.nterms = nvec;
   const bool to_host = (result_host != nullptr) && scope != 2;
   const ResOut out   = next_out(ctx, 0, to_host);
-  if (n <= ctx->tune.exact_threshold) launch_k(ctx, k_lincomb_sqnorm_exact, dim3(1), dim3(kBlock), a, (int)n, out, xa);
-  else
-  {
-    int W = wmax;
-    if (ctx->tune.vec_width > 0 && ctx->tune.vec_width < W) W = (int)ctx->tune.vec_width;
-    int64_t tiles = n / ((int64_t)kBlock * W);
-    if (tiles < 1) tiles = 1;
-    int64_t cap = (int64_t)kSMs * 4; /* 4 CTAs of 256 threads per SM (60 registers): one resident wave */
-    if (ctx->tune.max_blocks != kMaxBlocksDef && cap > ctx->tune.max_blocks) cap = ctx->tune.max_blocks;
-    const int grid = (int)((tiles < cap) ? tiles : cap);
-    if (W == 4) launch_k(ctx, k_lincomb_sqnorm<4>, dim3(grid), dim3(kBlock), a, n, ctx->d_tagged, out, xa);
-    else if (W == 2) launch_k(ctx, k_lincomb_sqnorm<2>, dim3(grid), dim3(kBlock), a, n, ctx->d_tagged, out, xa);
-    else launch_k(ctx, k_lincomb_sqnorm<1>, dim3(grid), dim3(kBlock), a, n, ctx->d_tagged, out, xa);
-  }
+  launch_lincomb_sqnorm(ctx, nvec, c, nullptr, X, z, n, out, xa);
   int rc = check_launch(ctx, "linear_combination_sqnorm");
   if (rc) return rc;
   if (scope == 2) return finish_global_nccl(ctx, 1, B200VEC_SUM, result_host);
   return finish_host(ctx, 0, 1, result_host);
+}
+
+/* One column of MODIFIED Gram-Schmidt (sundials_iterative.c:45-80) as a chain of nproj + 1 kernels and
+   ONE host wait:  res[0] = v_k . v_k,  h_0 = V_0 . v_k          (2-wide multi-dot, v_k read once)
+                   v_k <- v_k - h_i V_i,  h_{i+1} = V_{i+1} . v_k  (k_reduce<RAxpyDot>, h_i read on the device)
+                   v_k <- v_k - h_{last} V_last,  ||v_k||^2        (k_lincomb_sqnorm, device coefficient)
+   h_host[nproj]; norms_host[0] = v_k . v_k before, norms_host[1] = after. */
+int b200vec_mgs_sweep(b200vec_ctx ctx, int nproj, double* vk, const double* const* V, int64_t n, double* h_host,
+                      double* norms_host)
+{
+  B200_CHECK_CTX(ctx);
+  if (nproj < 1 || nproj + 2 > kMaxRows || n < 0 || !V || !h_host || !norms_host || (n > 0 && !vk))
+  {
+    ctx->scope_global = false;
+    return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__);
+  }
+  DeviceGuard g(ctx->device);
+  Chain ch(ctx, true);
+  if (n == 0 && ch.scope == 0)
+  {
+    for (int i = 0; i < nproj; i++) h_host[i] = 0.0;
+    norms_host[0] = norms_host[1] = 0.0;
+    return B200VEC_OK;
+  }
+  int rc;
+  {
+    MultiArgs m;
+    m.shared = vk;
+    m.nout   = 2;
+    m.self_j = 0;
+    for (int j = 0; j < kMaxOut; j++) m.A[j] = nullptr;
+    for (int j = 0; j < kMaxPair; j++) m.B[j] = nullptr;
+    m.A[0] = vk;
+    m.A[1] = V[0];
+    const long long t = ch.advance();
+    rc = launch_multi_group<0>(ctx, "mgs_sweep(norm, h0)", m, n, 0, ch.to_host, ch.xa, t);
+    if (!rc) rc = ch.after(0, 2);
+    if (rc) return rc;
+  }
+  for (int i = 0; i + 1 < nproj; i++)
+  {
+    const ResOut out = ch.next(2 + i);
+    rc = launch_reduce_kernel(ctx, "mgs_sweep(axpy_dot)", RAxpyDot{0.0, ctx->d_result + 1 + i},
+                              RedPtrs{V[i], vk, V[i + 1], vk}, n, out, ch.xa);
+    if (!rc) rc = ch.after(2 + i, 1);
+    if (rc) return rc;
+  }
+  {
+    const double* X2[2] = {vk, V[nproj - 1]};
+    const ResOut out    = ch.next(nproj + 1);
+    launch_lincomb_sqnorm(ctx, 2, nullptr, ctx->d_result + nproj, X2, vk, n, out, ch.xa);
+    rc = check_launch(ctx, "mgs_sweep(last update, norm)");
+    if (!rc) rc = ch.after(nproj + 1, 1);
+    if (rc) return rc;
+  }
+  double res[kMaxRows];
+  rc = ch.finish(nproj + 2, res);
+  if (rc) return rc;
+  norms_host[0] = res[0];
+  for (int i = 0; i < nproj; i++) h_host[i] = res[1 + i];
+  norms_host[1] = res[nproj + 1];
+  return B200VEC_OK;
+}
+
+/* One column of CLASSICAL Gram-Schmidt (sundials_iterative.c:130-146) as a chain of 2 kernels and ONE host wait:
+     dots_j = x . Ydots_j, j < nvec          (multi-dot; x itself may be among the Ydots and is then read once)
+     z <- Xcomb_0 - sum_j dots_{j-1} Xcomb_j, ||z||^2   (k_lincomb_sqnorm with device coefficients c_0 = 1,
+                                                         c_j = -dots_{j-1}; nvec terms, z may alias Xcomb_0)
+   dots_host[nvec]; *sqnorm_host = z . z. */
+int b200vec_cgs_step(b200vec_ctx ctx, int nvec, const double* x, const double* const* Ydots, const double* const* Xcomb,
+                     double* z, int64_t n, double* dots_host, double* sqnorm_host)
+{
+  B200_CHECK_CTX(ctx);
+  if (nvec < 2 || nvec > kMaxOut || nvec > kLcnMaxTerms || nvec + 1 > kMaxRows || n < 0 || !Ydots || !Xcomb || !dots_host ||
+      !sqnorm_host || (n > 0 && (!x || !z)))
+  {
+    ctx->scope_global = false;
+    return set_error(B200VEC_ERR_ARG, "%s: bad argument", __func__);
+  }
+  DeviceGuard g(ctx->device);
+  Chain ch(ctx, true);
+  if (n == 0 && ch.scope == 0)
+  {
+    for (int i = 0; i < nvec; i++) dots_host[i] = 0.0;
+    *sqnorm_host = 0.0;
+    return B200VEC_OK;
+  }
+  int rc;
+  /* the multi-dot, in groups only on the exact-order path (the staged terms of a group must fit shared
+     memory: bit-identical results for n <= exact_threshold whatever nvec is) */
+  int group = kMaxOut;
+  if (n > 0 && n <= ctx->tune.exact_threshold)
+  {
+    int fit = (int)(kExactMaxElems / n);
+    if (fit < 1) fit = 1;
+    if (fit < group) group = fit;
+  }
+  for (int j0 = 0; j0 < nvec; j0 += group)
+  {
+    MultiArgs m;
+    m.shared = x;
+    m.nout   = (nvec - j0 < group) ? nvec - j0 : group;
+    m.self_j = -1;
+    for (int j = 0; j < kMaxOut; j++)
+    {
+      m.A[j] = (j < m.nout) ? Ydots[j0 + j] : nullptr;
+      if (m.self_j < 0 && j < m.nout && m.A[j] == x) m.self_j = j;
+    }
+    for (int j = 0; j < kMaxPair; j++) m.B[j] = nullptr;
+    const long long t = ch.advance();
+    rc = launch_multi_group<0>(ctx, "cgs_step(dots)", m, n, j0, ch.to_host, ch.xa, t);
+    if (!rc) rc = ch.after(j0, m.nout);
+    if (rc) return rc;
+  }
+  {
+    const ResOut out = ch.next(nvec);
+    launch_lincomb_sqnorm(ctx, nvec, nullptr, ctx->d_result, Xcomb, z, n, out, ch.xa);
+    rc = check_launch(ctx, "cgs_step(combination, norm)");
+    if (!rc) rc = ch.after(nvec, 1);
+    if (rc) return rc;
+  }
+  double res[kMaxRows];
+  rc = ch.finish(nvec + 1, res);
+  if (rc) return rc;
+  for (int i = 0; i < nvec; i++) dots_host[i] = res[i];
+  *sqnorm_host = res[nvec];
+  return B200VEC_OK;
 }
 
 } /* extern "C" */

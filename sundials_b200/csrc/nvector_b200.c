@@ -785,6 +785,39 @@ SUNErrCode N_VAxpyDot_B200(sunrealtype a, N_Vector x, N_Vector z, N_Vector w, su
   return map_err(rc);
 }
 
+/* one modified Gram-Schmidt column as a chain of nproj + 1 kernels with ONE host wait (b200vec_mgs_sweep) */
+SUNErrCode N_VModifiedGSSweep_B200(int nproj, N_Vector* V, N_Vector vk, sunrealtype* h, sunrealtype* norms)
+{
+  if (nproj < 1 || !h || !norms) return SUN_ERR_ARG_OUTOFRANGE;
+  ptr_table tv;
+  if (gather(&tv, V, nproj)) return SUN_ERR_MALLOC_FAIL;
+  int rc = NDIST(vk) ? b200vec_ctx_set_scope(NCTX(vk), B200VEC_SCOPE_GLOBAL) : B200VEC_OK;
+  if (!rc) rc = b200vec_mgs_sweep(NCTX(vk), nproj, NDEV(vk), tv.p, NLEN(vk), h, norms);
+  table_free(&tv);
+  if (!rc) coherent_sync(vk);
+  return map_err(rc);
+}
+
+/* one classical Gram-Schmidt column as a chain of 2 kernels with ONE host wait (b200vec_cgs_step) */
+SUNErrCode N_VClassicalGSStep_B200(int nvec, N_Vector x, N_Vector* Ydots, N_Vector* Xcomb, N_Vector z,
+                                   sunrealtype* dots, sunrealtype* sqnorm)
+{
+  if (nvec < 2 || !dots || !sqnorm) return SUN_ERR_ARG_OUTOFRANGE;
+  ptr_table ty, tx;
+  if (gather(&ty, Ydots, nvec)) return SUN_ERR_MALLOC_FAIL;
+  if (gather(&tx, Xcomb, nvec))
+  {
+    table_free(&ty);
+    return SUN_ERR_MALLOC_FAIL;
+  }
+  int rc = NDIST(z) ? b200vec_ctx_set_scope(NCTX(z), B200VEC_SCOPE_GLOBAL) : B200VEC_OK;
+  if (!rc) rc = b200vec_cgs_step(NCTX(z), nvec, NDEV(x), ty.p, tx.p, NDEV(z), NLEN(z), dots, sqnorm);
+  table_free(&ty);
+  table_free(&tx);
+  if (!rc) coherent_sync(z);
+  return map_err(rc);
+}
+
 SUNErrCode N_VScaleAddMulti_B200(int nvec, sunrealtype* a, N_Vector x, N_Vector* Y, N_Vector* Z)
 {
   if (nvec < 1) return SUN_ERR_ARG_OUTOFRANGE;

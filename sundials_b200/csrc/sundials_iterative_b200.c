@@ -7,6 +7,8 @@
 #include <math.h>
 
 #define FACTOR 1000.0 /* ref:30 */
+#define B200_MGS_CHAIN_MAX 60 /* longest sweep one chain handles (result slots per context - 2) */
+#define B200_GS_CHAIN_MAX 24 /* widest column one chain handles (multi-dot outputs per launch) */
 
 static long g_calls = 0;
 long SUNClassicalGS_B200_Calls(void) { return g_calls; }
@@ -22,24 +24,36 @@ SUNErrCode SUNClassicalGS_B200(N_Vector* v, sunrealtype** h, int k, int p, sunre
   sunrealtype sq = 0.0;
   g_calls++;
 
-  /* all projections and v[k].v[k] in ONE multi-dot (ref:130); x = v[k] is itself the last Y, the
-     kernel reads it once */
-  err = N_VDotProdMulti_B200(k - i0 + 1, v[k], v + i0, stemp);
-  if (err) return err;
-
-  const sunrealtype vk_norm = rsqrt_guard(stemp[k - i0]);
-  for (int i = k - i0 - 1; i >= 0; i--) /* ref:133-138, including its indexing of h and v from 0 */
+  const int nvec = k - i0 + 1;
+  /* operands of the combination in the reference's order (ref:133-140, including its indexing of h
+     and v from 0): vtemp = {v[k], v[0], v[1], ...} */
+  for (int i = nvec - 2; i >= 0; i--) vtemp[i + 1] = v[i];
+  vtemp[0] = v[k];
+  if (nvec <= B200_GS_CHAIN_MAX)
+  {
+    /* ONE chain, one host wait: the (k+1)-wide multi-dot (ref:130; x = v[k] is itself the last Y and is read
+       once), then v[k] <- v[k] - sum h_i v_i together with ||v[k]||^2 (ref:142 + ref:146) with the
+       coefficients -h_i taken from the device result slots */
+    err = N_VClassicalGSStep_B200(nvec, v[k], v + i0, vtemp, v[k], stemp, &sq);
+    if (err) return err;
+  }
+  else
+  {
+    err = N_VDotProdMulti_B200(nvec, v[k], v + i0, stemp);
+    if (err) return err;
+  }
+  const sunrealtype vk_norm = rsqrt_guard(stemp[nvec - 1]);
+  for (int i = nvec - 2; i >= 0; i--)
   {
     h[i][k_minus_1] = stemp[i];
     stemp[i + 1]    = -stemp[i];
-    vtemp[i + 1]    = v[i];
   }
   stemp[0] = 1.0;
-  vtemp[0] = v[k];
-
-  /* v[k] <- v[k] - sum h_i v_i  and  ||v[k]||^2 of the result, one pass (ref:142 + ref:146) */
-  err = N_VLinearCombinationSqNorm_B200(k - i0 + 1, stemp, vtemp, v[k], &sq);
-  if (err) return err;
+  if (nvec > B200_GS_CHAIN_MAX)
+  {
+    err = N_VLinearCombinationSqNorm_B200(nvec, stemp, vtemp, v[k], &sq);
+    if (err) return err;
+  }
   *new_vk_norm = rsqrt_guard(sq);
 
   /* re-orthogonalise if the new vector is tiny against the old one (ref:151-168) */
@@ -80,27 +94,41 @@ SUNErrCode SUNModifiedGS_B200(N_Vector* v, sunrealtype** h, int k, int p, sunrea
     return SUN_SUCCESS;
   }
 
-  /* ||v_k||^2 and the first projection in one 2-wide multi-dot (ref:52 + first pass of ref:62) */
-  N_Vector y2[2] = {v[k], v[i0]};
-  err = N_VDotProdMulti_B200(2, v[k], y2, d2);
-  if (err) return err;
-  const sunrealtype vk_norm = rsqrt_guard(d2[0]);
-  hi                        = d2[1];
-
-  for (int i = i0; i < k; i++) /* ref:60-66 */
+  sunrealtype vk_norm;
+  if (k - i0 <= B200_MGS_CHAIN_MAX)
   {
-    h[i][k_minus_1] = hi;
-    if (i + 1 < k)
-    { /* v_k <- v_k - h_i v_i, and h_{i+1} = v_{i+1} . v_k on the updated vector */
-      err = N_VAxpyDot_B200(-hi, v[i], v[k], v[i + 1], &hi);
-      if (err) return err;
-    }
-    else
-    { /* last update together with the new norm (ref:70) */
-      sunrealtype c2[2] = {1.0, -hi};
-      N_Vector x2[2]    = {v[k], v[i]};
-      err               = N_VLinearCombinationSqNorm_B200(2, c2, x2, v[k], &sq);
-      if (err) return err;
+    /* the whole column as ONE chain of k - i0 + 1 kernels and one host wait: every kernel reads the
+       projection it needs from the device result slot its predecessor wrote */
+    sunrealtype hcol[B200_MGS_CHAIN_MAX], norms[2];
+    err = N_VModifiedGSSweep_B200(k - i0, v + i0, v[k], hcol, norms);
+    if (err) return err;
+    for (int i = i0; i < k; i++) h[i][k_minus_1] = hcol[i - i0];
+    vk_norm = rsqrt_guard(norms[0]);
+    sq      = norms[1];
+  }
+  else
+  {
+    /* ||v_k||^2 and the first projection in one 2-wide multi-dot (ref:52 + first pass of ref:62) */
+    N_Vector y2[2] = {v[k], v[i0]};
+    err = N_VDotProdMulti_B200(2, v[k], y2, d2);
+    if (err) return err;
+    vk_norm = rsqrt_guard(d2[0]);
+    hi      = d2[1];
+    for (int i = i0; i < k; i++) /* ref:60-66 */
+    {
+      h[i][k_minus_1] = hi;
+      if (i + 1 < k)
+      { /* v_k <- v_k - h_i v_i, and h_{i+1} = v_{i+1} . v_k on the updated vector */
+        err = N_VAxpyDot_B200(-hi, v[i], v[k], v[i + 1], &hi);
+        if (err) return err;
+      }
+      else
+      { /* last update together with the new norm (ref:70) */
+        sunrealtype c2[2] = {1.0, -hi};
+        N_Vector x2[2]    = {v[k], v[i]};
+        err               = N_VLinearCombinationSqNorm_B200(2, c2, x2, v[k], &sq);
+        if (err) return err;
+      }
     }
   }
   *new_vk_norm = rsqrt_guard(sq);

@@ -143,6 +143,66 @@ def main():
             if not np.array_equal(P.host(z, nl).view(np.uint64), zo[a:b].view(np.uint64)):
                 fails += 1
                 print(f"[rank {rank}] MISMATCH linear_sum block")
+        # fused Gram-Schmidt pieces on the distributed vectors, against the oracle on the WHOLE vectors:
+        # (a) combination + squared norm, (b) update + next projection, (c) whole chained columns
+        lib.N_VLinearCombinationSqNorm_B200.restype = C.c_int
+        lib.N_VLinearCombinationSqNorm_B200.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p),
+                                                        C.c_void_p, C.POINTER(C.c_double)]
+        lib.N_VAxpyDot_B200.restype = C.c_int
+        lib.N_VAxpyDot_B200.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        lib.N_VModifiedGSSweep_B200.restype = C.c_int
+        lib.N_VModifiedGSSweep_B200.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_double),
+                                                C.POINTER(C.c_double)]
+        lib.N_VClassicalGSStep_B200.restype = C.c_int
+        lib.N_VClassicalGSStep_B200.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        sq, dd = C.c_double(), C.c_double()
+        gz = gx.copy()
+        zz = mk(gz)
+        cc = [1.0, -0.37, 0.61]
+        assert lib.N_VLinearCombinationSqNorm_B200(3, P.coefs(cc), P.varray([zz, y, w]), zz, C.byref(sq)) == 0
+        orc.linear_combination(cc, [gz, gy, gw], gz)
+        close("LinearCombinationSqNorm", sq.value, orc.dot_prod(gz, gz), orc.dot_prod(gz, gz))
+        assert lib.N_VAxpyDot_B200(-0.25, y, zz, w, C.byref(dd)) == 0
+        orc.linear_sum(1.0, gz, -0.25, gy, gz)
+        close("AxpyDot", dd.value, orc.dot_prod(gw, gz), np.abs(gw * gz).sum())
+        # modified sweep against {y, w} and classical step against {y, w, zz}: mirror the reference's op sequence
+        hcol, nrm2 = (C.c_double * 2)(), (C.c_double * 2)()
+        assert lib.N_VModifiedGSSweep_B200(2, P.varray([y, w]), zz, hcol, nrm2) == 0
+        want_n0 = orc.dot_prod(gz, gz)
+        h0 = orc.dot_prod(gy, gz)
+        orc.linear_sum(1.0, gz, -h0, gy, gz)
+        h1 = orc.dot_prod(gw, gz)
+        orc.linear_sum(1.0, gz, -h1, gw, gz)
+        close("MGS sweep v.v", nrm2[0], want_n0, want_n0)
+        close("MGS sweep h0", hcol[0], h0, np.abs(gy * gz).sum() + abs(h0))
+        close("MGS sweep h1", hcol[1], h1, np.abs(gw * gz).sum() + abs(h1) + abs(h0) * np.abs(gw * gy).sum())
+        close("MGS sweep norm", nrm2[1], orc.dot_prod(gz, gz), orc.dot_prod(gz, gz))
+        if nl > 0:      # the vector itself stayed within rounding of the serial sequence
+            P.from_device(zz)
+            if not np.allclose(P.host(zz, nl), gz[a:b], rtol=0, atol=1e-12 * max(1.0, float(np.abs(gz).max()))):
+                fails += 1
+                print(f"[rank {rank}] MISMATCH modified Gram-Schmidt sweep vector block")
+        # classical step on a fresh vector: dots against {y, w, itself}, then the combination + norm
+        gq = gx.copy()
+        q = mk(gq)
+        d3 = (C.c_double * 3)()
+        assert lib.N_VClassicalGSStep_B200(3, q, P.varray([y, w, q]), P.varray([q, y, w]), q, d3, C.byref(sq)) == 0
+        wd = orc.dot_prod_multi(gq, [gy, gw, gq])
+        for j, g2 in enumerate((gy, gw, gq)):
+            close(f"CGS step dots[{j}]", d3[j], wd[j], np.abs(gq * g2).sum())
+        orc.linear_combination([1.0, -wd[0], -wd[1]], [gq, gy, gw], gq)
+        wn = orc.dot_prod(gq, gq)
+        if abs(sq.value - wn) > 1e-10 * wn:   # the coefficients differ in their last bits: amplified by |d| |y| / |z|
+            fails += 1
+            print(f"[rank {rank}] MISMATCH CGS step norm: {sq.value!r} vs {wn!r}")
+        if nl > 0:
+            P.from_device(q)
+            if not np.allclose(P.host(q, nl), gq[a:b], rtol=0, atol=1e-10 * max(1.0, float(np.abs(gq).max()))):
+                fails += 1
+                print(f"[rank {rank}] MISMATCH classical Gram-Schmidt step vector block")
+        P.Destroy(q)
+        P.Destroy(zz)
         # identical scalars on every rank (integrators must branch identically)
         v = torch.tensor([P.WrmsNorm(x, w)], dtype=torch.float64, device="cuda")
         lst = [torch.zeros_like(v) for _ in range(world)]
