@@ -607,6 +607,36 @@ def workload_config(args):
 # --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run this rank's host thread (and therefore its pinned allocations, which
+    follow the first-touch / local NUMA policy) on the NUMA node the GPU's PCIe link hangs off.  With 8
+    ranks uploading 1 GiB per step each, pinned buffers on the wrong socket turn the PCIe copies into
+    cross-socket traffic.  Best effort: any failure leaves the affinity untouched."""
+    try:
+        r = subprocess.run(["nvidia-smi", f"--id={local_rank}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                           capture_output=True, text=True, timeout=20)
+        bus = r.stdout.strip().lower()
+        if not bus:
+            return None
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:   # nvidia-smi prints an 8-digit PCI domain
+            bus = bus[4:]
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return {"node": node, "bound": False}
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus), "bound": True}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "error": f"{type(e).__name__}: {e}"}
+
+
+
 def b200_vectors(P, lib, ctx, n, world, rank, nv=NVECS, ns=NSUMS, keep_host_x=True, seed=1234):
     """the suite's vectors on NVECTOR_B200 (device memory), same data as cpu_vectors(): four base
     arrays are uploaded once and every vector is scale(i) * base, formed ON the device by N_VScale;
@@ -769,6 +799,7 @@ def b200_arm(args):
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
+    numa = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else None
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -1049,6 +1080,18 @@ def b200_arm(args):
             cpu = {"value": round(g_omp, 2), "unit": "GB/s", "cores": threads, "kind": "reference",
                    "sample": sample_omp + " (bounded sample of the workload)", "serial_1core_GBs": round(g_ser, 2),
                    "serial_sample": sample_ser}
+            # the same step on the same data at the sample's length on the GPU: the suite's result checksum
+            # (WRMS norm of the last output vector) must agree with the reference's own vector
+            v2 = b200_vectors(P, lib, ctx, 1 << args.cpu_log2n, 1, 0, keep_host_x=False)
+            s2 = Suite(perf, v2)
+            s2.step(1)
+            s2.check()
+            mine = s2.result("N_VWrmsNorm(result)")
+            for v in all_handles(v2):
+                P.Destroy(v)
+            cpu["checksum_parity"] = {"length": f"2^{args.cpu_log2n}", "b200": mine, "reference_nvector_openmp": chk,
+                                      "rel_diff": abs(mine - chk) / abs(chk) if chk else None,
+                                      "ok": bool(chk) and abs(mine - chk) <= 1e-13 * abs(chk)}
         except Exception as e:  # the baseline is reported, never required
             cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "reference",
                    "sample": f"unavailable: {e}"}
@@ -1079,6 +1122,8 @@ def b200_arm(args):
         legs["sweep"] = sw
     red = ["N_VDotProd", "N_VMaxNorm", "N_VMin", "N_VL1Norm", "N_VWrmsNorm", "N_VWrmsNormMask", "N_VInvTest",
            "N_VConstrMask", "N_VMinQuotient"]
+    if cpu and "checksum_parity" in cpu:
+        legs["checksum_vs_reference_ok"] = cpu["checksum_parity"]["ok"]
     legs["reductions_api_frac"] = {k[3:]: per_op[k]["frac_of_peak"] for k in red}
     legs["reductions_dev_frac"] = {k[3:]: per_op[k].get("dev_frac_of_peak") for k in red}
 
@@ -1096,6 +1141,7 @@ def b200_arm(args):
         "cpu_baseline": cpu,
         "clocks": clocks,
         "reduction_transport": lib.b200vec_comm_transport(ctx).decode(),
+        "numa": numa,
         "result_checksum": result_value,
         "ops_per_step": suite.nops,
         "dist_parity": parity,
@@ -1135,6 +1181,7 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="full length sweep 2^16 .. 2^30 with CPU columns up to 2^26")
     ap.add_argument("--no-cvdiurnal", action="store_true", help="skip the CVODE cvDiurnal_kry leg")
     ap.add_argument("--only-suite", action="store_true", help="op suite only: skip every leg")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
