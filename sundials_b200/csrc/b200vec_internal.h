@@ -81,7 +81,9 @@ struct b200vec_ctx_s
   cudaStream_t stream   = nullptr;
   int refcount          = 1;
   b200::Tuning tune;
-  int64_t launches      = 0;
+  int64_t launches      = 0;      /* resettable ("count_launches" tuning key)        */
+  int64_t launches_total = 0;     /* since the context was created (B200VEC_REPORT)  */
+  double t_created       = 0.0;
 
   /* reduction workspace (device) */
   double* d_partials    = nullptr; /* [kMaxOut][kMaxPartialBlocks]  (multi-output kernels, ticket scheme) */
