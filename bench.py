@@ -940,7 +940,7 @@ def b200_arm(args):
     reps = 10
     for i, name in enumerate(suite.names):
         suite.op(i, 1)
-        torch.cuda.synchronize()
+        barrier()   # the streaming ops before a collective op let the ranks drift apart: start each op aligned
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         suite.op(i, reps)
