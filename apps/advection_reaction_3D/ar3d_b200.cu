@@ -687,7 +687,8 @@ void b200_ar3d_default_opts(b200_ar3d_opts* o)
   o->nout       = 10;
   o->save       = 0;
   strcpy(o->outputdir, ".");
-  o->output = 1;
+  o->output    = 1;
+  o->fused_ewt = 1;
 }
 
 int b200_ar3d_plan_create(b200vec_ctx ctx, const b200_ar3d_opts* opts, b200_ar3d_plan* out)
@@ -955,6 +956,7 @@ struct Driver
      (N_VGetLocalVector_MPIPlusX in arkode_driver.cpp:559-602) */
   std::vector<std::pair<N_Vector, N_Vector>> local_views;
   void* arkode_mem = nullptr;
+  double rtol = 0.0, atol = 0.0; /* for the fused error-weight function */
 };
 
 double* dptr(N_Vector v) { return N_VGetDeviceArrayPointer_B200(v); }
@@ -972,6 +974,14 @@ int f_advection_reaction(sunrealtype, N_Vector y, N_Vector ydot, void* ud)
 {
   return b200_ar3d_rhs(((Driver*)ud)->p, AR3D_RHS_ADVECTION_REACTION, dptr(y), dptr(ydot));
 }
+/* ARKEwtFn / CVEwtFn: ewt = 1 / (rtol |y| + atol) in one kernel, the bits of arkEwtSetSS (arkode.c:2935-2947)
+   and cvEwtSetSS (cvode.c:4794-4822) */
+int ewt_cb(N_Vector y, N_Vector ewt, void* ud)
+{
+  auto* d = (Driver*)ud;
+  return N_VEwtSet_B200(d->rtol, d->atol, nullptr, d->atol == 0.0, y, ewt);
+}
+
 /* rhs3D.hpp:672-686 */
 int psolve_cb(sunrealtype, N_Vector y, N_Vector, N_Vector r, N_Vector z, sunrealtype gamma, sunrealtype, int, void* ud)
 {
@@ -1191,6 +1201,8 @@ extern "C" int b200_ar3d_run(b200vec_ctx ctx, const b200_ar3d_opts* opts, b200_a
   /* ParseArgs, advection_reaction_3D.cpp:432-437 */
   if (o.method == AR3D_METHOD_CV_ADAMS) o.nls = AR3D_NLS_FIXEDPOINT;
   Driver d;
+  d.rtol = o.rtol;
+  d.atol = o.atol;
   if (b200_ar3d_plan_create(ctx, &o, &d.p)) return -1;
   b200_ar3d_plan p = d.p;
   CHK(SUNContext_Create(SUN_COMM_NULL, &d.sunctx), "SUNContext_Create");
@@ -1303,6 +1315,9 @@ extern "C" int b200_ar3d_run(b200vec_ctx ctx, const b200_ar3d_opts* opts, b200_a
     CHK(ARKodeSetOrder(mem, o.order), "ARKodeSetOrder");
     CHK(ARKodeSetUserData(mem, &d), "ARKodeSetUserData");
     CHK(ARKodeSStolerances(mem, o.rtol, o.atol), "ARKodeSStolerances");
+    /* implicit / IMEX: the built-in routine would be arkEwtSetSS (the fixed-step ERK path above keeps the
+       built-in choice: ARKODE swaps in arkEwtSetSmallReal there, arkode_erkstep.c:423) */
+    if (o.fused_ewt) CHK(ARKodeWFtolerances(mem, ewt_cb), "ARKodeWFtolerances");
     CHK(ARKodeSetMaxNumSteps(mem, 100000), "ARKodeSetMaxNumSteps");
     if (o.nls == AR3D_NLS_NEWTON)
     {
@@ -1342,6 +1357,7 @@ extern "C" int b200_ar3d_run(b200vec_ctx ctx, const b200_ar3d_opts* opts, b200_a
     CHK(CVodeInit(mem, f_advection_reaction, o.t0, y), "CVodeInit");
     CHK(CVodeSetUserData(mem, &d), "CVodeSetUserData");
     CHK(CVodeSStolerances(mem, o.rtol, o.atol), "CVodeSStolerances");
+    if (o.fused_ewt) CHK(CVodeWFtolerances(mem, ewt_cb), "CVodeWFtolerances");
     CHK(CVodeSetMaxNumSteps(mem, 100000), "CVodeSetMaxNumSteps");
     if (o.method == AR3D_METHOD_CV_BDF && o.nls == AR3D_NLS_NEWTON)
     {

@@ -70,6 +70,9 @@ typedef struct
   int output;       /* 0: silent, 1: the reference's screen output on rank 0 (1)                */
   int force_generic;/* 1: always use the one-node-per-thread kernel (testing)            (0)   */
   int planes_per_cta; /* fast RHS kernel: x-planes marched per CTA, 0 = default          (0)   */
+  int fused_ewt;    /* implicit / IMEX ARKODE and CVODE runs: error weights by ONE kernel (N_VEwtSet_B200 as the
+                       EwtFn registered with ARKodeWFtolerances / CVodeWFtolerances) instead of the five
+                       vector ops of arkEwtSetSS / cvEwtSetSS; same bits                  (1)   */
 } b200_ar3d_opts;
 
 typedef struct

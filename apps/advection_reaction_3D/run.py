@@ -37,7 +37,7 @@ class Opts(C.Structure):
                 ("order", C.c_int), ("fpaccel", C.c_int), ("precond", C.c_int), ("fused", C.c_int),
                 ("t0", C.c_double), ("tf", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
                 ("nout", C.c_int), ("save", C.c_int), ("outputdir", C.c_char * 1024), ("output", C.c_int),
-                ("force_generic", C.c_int), ("planes_per_cta", C.c_int)]
+                ("force_generic", C.c_int), ("planes_per_cta", C.c_int), ("fused_ewt", C.c_int)]
 
 
 class Stats(C.Structure):

@@ -669,6 +669,7 @@ void b200_diffusion2d_default_opts(b200_diffusion2d_opts* o)
   o->nout         = 20;
   o->fused_ops    = 1;
   o->rows_per_cta = 0;
+  o->fused_ewt    = 1;
 }
 
 int b200_diffusion2d_plan_create(b200vec_ctx ctx, const b200_diffusion2d_opts* opts, b200_diffusion2d_plan* out)
@@ -894,6 +895,13 @@ int rhs_cb(sunrealtype t, N_Vector u, N_Vector f, void* user_data)
 }
 
 /* preconditioner_jacobi.cpp:25-61 */
+/* ARKEwtFn: ewt = 1 / (rtol |y| + atol) in one kernel, the bits of arkEwtSetSS (arkode.c:2935-2947) */
+int ewt_cb(N_Vector y, N_Vector ewt, void* user_data)
+{
+  auto* p = (b200_diffusion2d_plan)user_data;
+  return N_VEwtSet_B200(p->o.rtol, p->o.atol, nullptr, p->o.atol == 0.0, y, ewt);
+}
+
 int psetup_cb(sunrealtype, N_Vector, N_Vector, sunbooleantype, sunbooleantype*, sunrealtype gamma, void* user_data)
 {
   auto* p         = (b200_diffusion2d_plan)user_data;
@@ -978,6 +986,9 @@ extern "C" int b200_diffusion2d_run(b200vec_ctx ctx, const b200_diffusion2d_opts
   if (!mem) return fail("ARKStepCreate");
   CHK(ARKodeSStolerances(mem, opts->rtol, opts->atol), "ARKodeSStolerances");
   CHK(ARKodeSetUserData(mem, p), "ARKodeSetUserData");
+  /* DIRK (implicit): the built-in error-weight routine would be arkEwtSetSS; the registered function
+     computes the same vector with one kernel instead of five */
+  if (opts->fused_ewt) CHK(ARKodeWFtolerances(mem, ewt_cb), "ARKodeWFtolerances");
   CHK(ARKodeSetLinearSolver(mem, LS, nullptr), "ARKodeSetLinearSolver");
   if (opts->preconditioning)
   {

@@ -49,6 +49,8 @@ typedef struct
   /* vector options */
   int fused_ops; /* N_VEnableFusedOps_B200 (1)                           */
   int rows_per_cta; /* RHS kernel: rows marched per CTA; 0 = one wave of equal row blocks (0) */
+  int fused_ewt;    /* error weights by ONE kernel (N_VEwtSet_B200 as the ARKEwtFn registered with
+                       ARKodeWFtolerances) instead of arkEwtSetSS's five vector ops; same bits (1) */
 } b200_diffusion2d_opts;
 
 typedef struct

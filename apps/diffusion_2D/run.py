@@ -31,7 +31,7 @@ class Opts(C.Structure):
                 ("atol", C.c_double), ("order", C.c_int), ("linear", C.c_int), ("ls_gmres", C.c_int),
                 ("preconditioning", C.c_int), ("liniters", C.c_int), ("msbp", C.c_int), ("epslin", C.c_double),
                 ("maxsteps", C.c_int), ("controller", C.c_char * 16), ("output", C.c_int), ("nout", C.c_int),
-                ("fused_ops", C.c_int), ("rows_per_cta", C.c_int)]
+                ("fused_ops", C.c_int), ("rows_per_cta", C.c_int), ("fused_ewt", C.c_int)]
 
 
 class Stats(C.Structure):

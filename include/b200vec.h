@@ -156,6 +156,13 @@ int b200vec_constr_mask(b200vec_ctx ctx, const double* c, const double* x, doubl
 int b200vec_min_quotient(b200vec_ctx ctx, const double* num, const double* denom, int64_t n,
                          double* result_host);
 
+/* w_i = 1 / (rtol |y_i| + atol_i) and *min_denominator_host = min_i (rtol |y_i| + atol_i): the error-weight
+ * vector of CVODE / ARKODE / IDA in one pass, bit-identical to the op sequence of cvEwtSetSS/SV
+ * (src/cvode/cvode.c:4794-4860: N_VAbs, N_VScale, N_VAddConst | N_VLinearSum, [N_VMin], N_VInv) -- what
+ * src/cvode/cvode_fused_gpu.cpp:62 fuses for nvector_cuda.  atol_vec == NULL: scalar atol. */
+int b200vec_ewt_set(b200vec_ctx ctx, double rtol, double atol, const double* atol_vec, const double* y,
+                    double* w, int64_t n, double* min_denominator_host);
+
 /* z <- a x + z (serial's Vaxpy form, serial:1734) and result = sum_i w_i z_i of the UPDATED z, one
  * pass: a modified Gram-Schmidt step -- N_VLinearSum(1, v_k, -h_i, v_i, v_k) + N_VDotProd(v_{i+1}, v_k),
  * src/sundials/sundials_iterative.c:62-67 -- at 32 B/elt instead of 24 + 16.  w may alias x. */

@@ -130,6 +130,11 @@ SUNErrCode N_VDotProdMulti_B200(int nvec, N_Vector x, N_Vector* Y, sunrealtype* 
 /* not an ops-table slot: z = sum c_i X_i and *sqnorm = z . z in ONE pass (used by
  * SUNClassicalGS_B200, include/sundials_iterative_b200.h) */
 SUNErrCode N_VLinearCombinationSqNorm_B200(int nvec, sunrealtype* c, N_Vector* X, N_Vector z, sunrealtype* sqnorm);
+/* not an ops-table slot: the integrators' error-weight vector ewt_i = 1 / (rtol |y_i| + atol_i) in ONE
+ * kernel (16 B/elt instead of the 5 vector ops, 72 B/elt, of cvEwtSetSS / arkEwtSetSS).  Call it from a
+ * CVEwtFn / ARKEwtFn / IDAEwtFn registered with CV/ARK/IDA...WFtolerances: same bits, same return
+ * convention (0, or -1 when atolmin0 and a denominator is not positive).  vatol == NULL: scalar atol. */
+int N_VEwtSet_B200(sunrealtype rtol, sunrealtype atol, N_Vector vatol, sunbooleantype atolmin0, N_Vector y, N_Vector ewt);
 /* not an ops-table slot: z <- a x + z and *dot = w . z of the updated z in ONE pass (used by
  * SUNModifiedGS_B200) */
 SUNErrCode N_VAxpyDot_B200(sunrealtype a, N_Vector x, N_Vector z, N_Vector w, sunrealtype* dot);

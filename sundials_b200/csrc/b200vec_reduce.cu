@@ -191,6 +191,31 @@ __device__ __forceinline__ void prepare_policy(RAxpyDot& r)
   if (r.a_dev) r.a = -__ldcg(r.a_dev);
 }
 
+/* error-weight vector of the integrators in ONE pass: w_i = 1 / (rtol |y_i| + atol_i), and the minimum
+   of the denominators (the integrators refuse a non-positive one when an absolute tolerance is zero).
+   Replaces N_VAbs + N_VScale + N_VAddConst (or N_VLinearSum) + [N_VMin] + N_VInv of cvEwtSetSS/SV
+   (src/cvode/cvode.c:4794-4860), arkEwtSetSS/SV (src/arkode/arkode.c:2935-2975), IDAEwtSetSS/SV -- the
+   op sequence src/cvode/cvode_fused_gpu.cpp:62 (cvEwtSetSS_kernel) fuses for nvector_cuda -- with the
+   same operation order, hence the same bits: 16 B/elt (24 with a vector atol) instead of 64 + 8.
+   p0 = y, p1 = vector atol (VEC), out = w. */
+template <bool VEC>
+struct REwt
+{
+  using Comb = CombMin;
+  static constexpr int NIN = VEC ? 2 : 1;
+  static constexpr bool HAS_OUT = true;
+  static constexpr bool NAN_HEAD = false;
+  static constexpr int MAXU = 2;
+  double rtol, atol;
+  __device__ double term(double y, double av, double, double& outv, bool& store) const
+  {
+    const double t = (rtol * fabs(y)) + (VEC ? av : atol);
+    store          = true;
+    outv           = 1.0 / t;
+    return t;
+  }
+};
+
 struct RedPtrs
 {
   const double* p0;
@@ -1237,6 +1262,17 @@ int b200vec_min_quotient(b200vec_ctx ctx, const double* num, const double* denom
   B200_RARGS(num && denom);
   return launch_reduce(ctx, "min_quotient", RMinQuot{}, RedPtrs{num, denom, nullptr, nullptr}, n, DBL_MAX,
                        result_host);
+}
+
+int b200vec_ewt_set(b200vec_ctx ctx, double rtol, double atol, const double* atol_vec, const double* y, double* w,
+                    int64_t n, double* min_denominator_host)
+{
+  B200_RARGS(y && w);
+  if (atol_vec)
+    return launch_reduce(ctx, "ewt_set(vector atol)", REwt<true>{rtol, 0.0}, RedPtrs{y, atol_vec, nullptr, w}, n, DBL_MAX,
+                         min_denominator_host);
+  return launch_reduce(ctx, "ewt_set", REwt<false>{rtol, atol}, RedPtrs{y, nullptr, nullptr, w}, n, DBL_MAX,
+                       min_denominator_host);
 }
 
 int b200vec_axpy_dot(b200vec_ctx ctx, double a, const double* x, double* z, const double* w, int64_t n,

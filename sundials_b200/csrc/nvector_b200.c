@@ -774,6 +774,21 @@ SUNErrCode N_VLinearCombinationSqNorm_B200(int nvec, sunrealtype* c, N_Vector* X
   return map_err(rc);
 }
 
+/* ewt = 1 / (rtol |y| + atol) in ONE kernel -- the body of a user error-weight function for
+   CVodeWFtolerances / ARKodeWFtolerances / IDAWFtolerances (the public hook of the UNMODIFIED integrators),
+   bit-identical to their built-in cvEwtSetSS/SV, arkEwtSetSS/SV sequences (5 vector ops).  vatol == NULL:
+   scalar atol.  Returns 0, or -1 when atolmin0 (some absolute tolerance is zero) and a denominator is <= 0,
+   exactly as the built-in routines do (src/cvode/cvode.c:4794-4860). */
+int N_VEwtSet_B200(sunrealtype rtol, sunrealtype atol, N_Vector vatol, sunbooleantype atolmin0, N_Vector y, N_Vector ewt)
+{
+  double mind = NAN;
+  GLOBAL_SCOPE(ewt);
+  CHECK_ON(ewt, b200vec_ewt_set(NCTX(ewt), rtol, atol, vatol ? NDEV(vatol) : NULL, NDEV(y), NDEV(ewt), NLEN(ewt), &mind));
+  coherent_sync(ewt);
+  if (mind != mind) return -1; /* the kernel did not run */
+  return (atolmin0 && mind <= 0.0) ? -1 : 0;
+}
+
 /* z <- a x + z and *dot = w . z(updated) (GLOBAL on a distributed vector): N_VLinearSum(1, z, a, x, z)
    + N_VDotProd(w, z) of a modified Gram-Schmidt sweep (sundials_iterative.c:62-67) in one kernel */
 SUNErrCode N_VAxpyDot_B200(sunrealtype a, N_Vector x, N_Vector z, N_Vector w, sunrealtype* dot)

@@ -396,3 +396,42 @@ def test_axpy_dot_matches_linear_sum_then_dot_prod(be, oracle, n):
             assert r.value == want, (a, r.value, want)
         else:
             assert abs(r.value - want) <= RTOL * float(np.abs(w * zo).sum()), (a, r.value, want)
+
+
+@pytest.mark.parametrize("n", [7, 1000, 1025, 300_001])
+def test_fused_error_weights_match_the_integrators_op_sequence(be, oracle, n):
+    """ewt = 1 / (rtol |y| + atol) in one kernel: the bits of cvEwtSetSS / arkEwtSetSS (N_VAbs, N_VScale,
+    N_VAddConst, N_VInv) and of the SV forms (N_VAbs, N_VLinearSum(rtol, ., 1, atol, .), N_VInv); the
+    returned minimum is N_VMin of the denominators (the integrators' atolmin0 test)"""
+    import ctypes as C
+
+    from sundials_b200 import nvector as nv
+    from sundials_b200._lib import check
+
+    rng = np.random.default_rng(n)
+    y = rng.uniform(-3, 3, n)
+    y[n // 3] = 0.0
+    va = rng.uniform(0.0, 1e-6, n)
+    rtol, atol = 1e-5, 1e-10
+    dy, dva, dw = (nv.N_VMake(torch.from_numpy(v.copy()).cuda(), be.ctx) for v in (y, va, np.zeros(n)))
+    lib, r = be.ctx.lib, C.c_double()
+    # scalar atol
+    check(lib.b200vec_ewt_set(be.ctx.h, rtol, atol, None, dy.ptr, dw.ptr, n, C.byref(r)), "ewt_set")
+    t = np.empty(n)
+    oracle.abs(y, t)
+    oracle.scale(rtol, t, t)
+    oracle.add_const(t, atol, t)
+    want_min = oracle.min(t)
+    w = np.empty(n)
+    oracle.inv(t, w)
+    assert np.array_equal(_bits(dw.data.cpu().numpy()), _bits(w)) and r.value == want_min
+    # vector atol
+    check(lib.b200vec_ewt_set(be.ctx.h, rtol, 0.0, dva.ptr, dy.ptr, dw.ptr, n, C.byref(r)), "ewt_set(vec)")
+    oracle.abs(y, t)
+    oracle.linear_sum(rtol, t, 1.0, va, t)
+    want_min = oracle.min(t)
+    oracle.inv(t, w)
+    assert np.array_equal(_bits(dw.data.cpu().numpy()), _bits(w)) and r.value == want_min
+    # atol = 0 and a zero component: the denominator minimum is 0 -> the integrators' "-1"
+    check(lib.b200vec_ewt_set(be.ctx.h, rtol, 0.0, None, dy.ptr, dw.ptr, n, C.byref(r)), "ewt_set(atol 0)")
+    assert r.value == 0.0
