@@ -384,11 +384,12 @@ def run_diffusion_cpu_reference(n=2048, tf=1e-5):
             "ns_per_node_per_ls_iter": round(dt / max(nli, 1) / (n * n) * 1e9, 3)}
 
 
-def run_ar3d(ctx, world, args):
+def run_ar3d(ctx, world, args, nls="newton", tf=None):
     """Bounded solve of the re-hosted benchmarks/advection_reaction_3D (apps/advection_reaction_3D)
     on the bench's own context: BASELINE config 5 -- npts^3 mesh (512^3 = 4.0e8 unknowns), slabs
-    in x over the ranks (STRONG scaling: the mesh is fixed), ARKODE IMEX-ARK order 3, Newton +
-    SPGMR with the reaction-block preconditioner, fused vector ops on."""
+    in x over the ranks (STRONG scaling: the mesh is fixed), ARKODE IMEX-ARK order 3, fused vector ops on,
+    with either nonlinear solver the config names: Newton + SPGMR with the reaction-block preconditioner,
+    or the Anderson-accelerated fixed point (3 vectors)."""
     sys.path.insert(0, str(ROOT / "apps" / "advection_reaction_3D"))
     import importlib.util
 
@@ -396,12 +397,14 @@ def run_ar3d(ctx, world, args):
     app = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(app)
     n = args.ar3d_npts
-    st = app.run(ctx, npts=n, method="ARK-IMEX", nls="newton", fused=1, tf=args.ar3d_tf, nout=1, output=0)
+    tf = args.ar3d_tf if tf is None else tf
+    st = app.run(ctx, npts=n, method="ARK-IMEX", nls=nls, fused=1, tf=tf, nout=1, output=0)
     ev = st["evolve_seconds"]
+    how = "Newton + SPGMR + block preconditioner" if nls == "newton" else "Anderson-accelerated fixed point (m = 3)"
     return {
         "workload": f"benchmarks/advection_reaction_3D re-host: {n}^3 mesh x 3 species = {st['neq']} unknowns, "
-                    f"slabs in x over {world} GPU(s) (strong scaling), ARKODE IMEX-ARK order 3, Newton + SPGMR + "
-                    f"block preconditioner, rtol 1e-6 atol 1e-9, fused ops, tf = {args.ar3d_tf} (bounded; the "
+                    f"slabs in x over {world} GPU(s) (strong scaling), ARKODE IMEX-ARK order 3, {how}, "
+                    f"rtol 1e-6 atol 1e-9, fused ops, tf = {tf} (bounded; the "
                     f"benchmark's default is tf = 10)",
         "scaling": "strong", "solve_s": round(ev, 4), "steps": st["nst"], "step_attempts": st["nst_a"],
         "fe_evals": st["nfe"], "fi_evals": st["nfi"], "nls_iters": st["nni"], "ls_iters": st["nli"],
@@ -700,6 +703,10 @@ def run_sweep(P, lib, perf, ctx, world, rank, dist, torch, peak, lengths, cpu_le
     out = {"ops": classes, "lengths": {}, "timing": "C driver loop, CUDA events; reps back to back on one operand set "
            "(> L2 from 2^22 x 3 operands on; smaller lengths are L2 / launch-latency figures)"}
     free, _ = torch.cuda.mem_get_info()
+    if dist is not None:   # every rank must pick the same vector count: the reductions are collectives
+        t = torch.tensor([float(free)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        free = int(t.item())
     for L in lengths:
         n = 1 << L
         nv = 8
@@ -1031,6 +1038,15 @@ def b200_arm(args):
             ar3d = {"unavailable": f"{type(e).__name__}: {e}"}
         if leg is not None:
             ar3d["clocks"] = leg.stop(world)
+        # the config's other nonlinear solver: Anderson-accelerated fixed point (no linear solver)
+        try:
+            # (the stiff reaction terms hold a fixed-point iteration to ~1e-5 steps: 4246 steps for tf = 0.05,
+            #  so this run is bounded much shorter than the Newton one; compare ms_per_step)
+            fp = run_ar3d(ctx, world, args, nls="fixedpoint", tf=args.ar3d_fp_tf)
+            ar3d["fixedpoint"] = {k: fp[k] for k in ("workload", "solve_s", "steps", "step_attempts", "fe_evals", "fi_evals",
+                                                       "nls_iters", "ms_per_step", "urms", "vrms", "wrms")}
+        except Exception as e:
+            ar3d["fixedpoint"] = {"unavailable": f"{type(e).__name__}: {e}"}
 
     # ---- Krylov Gram-Schmidt built on the ops: the reference's unmodified
     # SUNClassicalGS / SUNModifiedGS, and the fused SUNClassicalGS_B200, on a basis of this vector; collective
@@ -1121,6 +1137,10 @@ def b200_arm(args):
         legs["advection_reaction_3D"] = {"solve_s": ar3d["solve_s"], "steps": ar3d["steps"], "fe": ar3d["fe_evals"],
                                          "nni": ar3d["nls_iters"], "nli": ar3d["ls_iters"],
                                          "sm_mhz_min": leg_clock_min(ar3d)}
+        fp = ar3d.get("fixedpoint") or {}
+        if "solve_s" in fp:
+            legs["advection_reaction_3D"]["fixedpoint"] = {"ms_per_step": fp["ms_per_step"], "steps": fp["steps"],
+                                                           "nni": fp["nls_iters"]}
     if gs and "b200" in gs:
         legs["gram_schmidt"] = {k: gs["b200"][k]["cycle_frac_of_peak"] for k in gs["b200"]}
     if cvd and "b200_pinned_s" in cvd:
@@ -1190,6 +1210,7 @@ def main():
     ap.add_argument("--no-ar3d", action="store_true", help="skip the ARKODE advection_reaction_3D leg")
     ap.add_argument("--ar3d-npts", type=int, default=512, help="GLOBAL mesh points per direction")
     ap.add_argument("--ar3d-tf", type=float, default=0.05)
+    ap.add_argument("--ar3d-fp-tf", type=float, default=5e-4, help="final time of the fixed-point variant of the leg")
     ap.add_argument("--no-gs", action="store_true", help="skip the Gram-Schmidt leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the (bounded) length sweep leg")
     ap.add_argument("--sweep", action="store_true", help="full length sweep 2^16 .. 2^30 with CPU columns up to 2^26")
