@@ -68,12 +68,15 @@ void* b200vec_ctx_get_stream(b200vec_ctx ctx);
 int b200vec_ctx_device(b200vec_ctx ctx);
 int b200vec_ctx_sync(b200vec_ctx ctx); /* cudaStreamSynchronize on the ctx stream */
 /* tuning knobs (sweepable from the bench without recompiling):
- *  "max_blocks"      grid cap of the reduction kernels (default 148*2 CTAs of 512 threads)
+ *  "max_blocks"      grid cap of the reduction kernels (default 148*2 CTAs of 512 threads; 148 below
+ *                    2^20 elements; one tile per CTA for the reductions that also write a vector)
  *  "pdl"             1 (default): programmatic dependent launch on every kernel
  *  "p2p"             1 (default): global reductions exchange over NVLink peer memory
  *                    inside the reduction kernel; 0: ncclAllReduce (same on all ranks!)
- *  "spin_wait"       1 (default): scalar-returning ops poll a pinned sequence word
+ *  "spin_wait"       1 (default): scalar-returning ops poll the tagged pinned result words
  *                    written by the kernel's final pass; 0: cudaStreamSynchronize
+ *  "profile"         1: %globaltimer counters (cross-rank waits; start / publication of the last
+ *                    reduction, armed by "prof_stamp_reset"); read "prof_counter_<i>"
  *  "stream_max_blocks" grid cap of streaming/fused kernels (default 0 = one tile per CTA)
  *  "vec_width"       doubles per load: 4 (256-bit LDG/STG), 2 (128-bit), 1; 0 = auto
  *  "unroll"          independent loads in flight per operand: 4, 2, 1; 0 = auto
@@ -124,11 +127,11 @@ int b200vec_compare(b200vec_ctx ctx, double c, const double* x, double* z, int64
 
 /* ------------------------------------------------------------------------
  * local reductions.  Each launches ONE two-stage kernel (per-thread sequential
- * partial -> warp shuffle -> block -> last-block-done fixed-order final pass)
- * that leaves the LOCAL result in the context's device result buffer
- * (b200vec_result_device) AND in a pinned host slot.
- *   result_host != NULL : the call synchronises the stream and stores the value
- *                         (what N_VDotProd etc. need: one sync, zero memcpys);
+ * partial -> warp shuffle -> block -> fixed-order final pass by CTA 0 over tagged
+ * CTA partials) that leaves the LOCAL result in the context's device result buffer
+ * (b200vec_result_device) AND, as two tagged 8-byte words, in pinned host memory.
+ *   result_host != NULL : the call waits for the tagged words and stores the value
+ *                         (what N_VDotProd etc. need: no stream sync, zero memcpys);
  *   result_host == NULL : asynchronous; combine across ranks with
  *                         b200vec_allreduce and read with b200vec_result_fetch.
  * Replaces the H2D-init + kernel + D2H + sync pattern of cuda:894-940,

@@ -3,28 +3,36 @@
  * Two-stage, single-launch, deterministic:
  *   stage 1  every thread folds its grid-stride share sequentially into W
  *            register accumulators (wide loads, U tiles in flight), folds those
- *            in fixed order, then warp shuffle tree -> 8 warp leaders -> CTA value,
- *            written to partials[blockIdx.x];
- *   stage 2  the last CTA to finish (ticket counter) folds partials[0..grid) in
- *            FIXED INDEX ORDER (thread t takes t, t+256, ...; then the same
- *            tree), so the result does not depend on which CTA happened to be
- *            last or on scheduling: run-to-run bitwise reproducible.  It stores
- *            the value to the context's device result slot and -- when the host
- *            wants the scalar -- to pinned, device-mapped host memory as ONE
- *            16-byte {value, sequence} store that the host polls: a
- *            scalar-returning N_Vector op needs no memcpy and no stream sync
- *            (the reference needs H2D + D2H + sync, nvector_cuda.cu:2277-2411)
- *            and no atomics on doubles (sundials_cuda_kernels.cuh:417-424 is
- *            order-nondeterministic).  Single-output kernels run 512 threads x
- *            2 CTAs/SM, the ticket is one acq_rel atomic (no separate fences):
- *            measured 24.9 us vs 27.5 us for 2^24 doubles
- *            (profiles/r01_mb_reduce_24b.txt).
+ *            in fixed order, then warp shuffle tree -> warp leaders -> CTA value;
+ *   stage 2  single-output kernels: every CTA stores its value as a TAGGED pair
+ *            (two 8-byte words, each (sequence << 32) | 32 value bits) into its slot
+ *            of the context's partials array; CTA 0 polls the slots until they carry
+ *            this launch's tag and folds them in FIXED INDEX ORDER (thread t takes
+ *            t, t+512, ...; then the same tree) -- no ticket atomic, no fence, the
+ *            finishing CTA is known in advance, and the result does not depend on
+ *            scheduling: run-to-run bitwise reproducible.  Multi-output kernels
+ *            (up to 24 outputs) keep a last-block-done ticket (one acq_rel atomic)
+ *            and let warp w of the last CTA fold outputs w, w + 8, ...
+ *            The value goes to the context's device result slot and -- when the host
+ *            wants the scalar -- as two tagged 8-byte words to pinned, device-mapped
+ *            host memory that the host polls: a scalar-returning N_Vector op needs no
+ *            memcpy, no stream sync, no system fence and no reliance on 16-byte store
+ *            atomicity (the reference needs H2D + D2H + sync, nvector_cuda.cu:2277-2411,
+ *            and atomics on doubles, sundials_cuda_kernels.cuh:417-424, which are
+ *            order-nondeterministic).  Measured (profiles/r02_reduce_attribution.md): 128 MiB
+ *            stream in 20.6-21.0 us device time = the measured HBM copy peak; the API call
+ *            adds 7.5-9 us of launch + PCIe that no kernel design removes.
  *
  * Exact-order path: for n <= exact_threshold (default 1024) one CTA stages the
  * per-element terms in shared memory and thread 0 adds them strictly
  * left-to-right -- bit-identical to nvector_serial.c's loops, which is what
  * keeps integrator step/iteration counts identical to the CPU reference on the
  * small regression problems (cvDiurnal_kry N=200, ark_heat2D N=1024).
+ *
+ * Fused forms built on the same epilogue: k_lincomb_sqnorm (linear combination + squared
+ * norm of its result), k_reduce<RAxpyDot> (update + next projection), k_reduce<REwt> (the
+ * integrators' error-weight vector), and the chained Gram-Schmidt sweeps that launch a
+ * whole column back to back with device-resident coefficients and ONE host wait.
  *
  * Arithmetic per term follows serial exactly (e.g. prodi = x*w; sum += prodi*prodi,
  * serial:664-665 -- NOT x*w*x*w as VectorKernels.cuh:167 computes).
