@@ -728,6 +728,20 @@ int b200_ar3d_plan_create(b200vec_ctx ctx, const b200_ar3d_opts* opts, b200_ar3d
   p->chunk         = opts->planes_per_cta > 0 ? opts->planes_per_cta : 8;
   if (const char* v = getenv("B200_AR3D_CHUNK"))
     if (atoi(v) > 0) p->chunk = atoi(v);
+  if (p->fast && p->np > 1)
+  {
+    /* The marching kernel gives the CTAs that push the slab's last plane the lowest block indices and the
+       CTAs that wait for the neighbour's plane the highest, but CUDA does not promise dispatch in index
+       order.  The exchange cannot dead-lock whatever the order as long as the waiting CTAs (one per plane
+       tile) cannot fill every resident CTA slot of the GPU: a free slot always goes to a CTA that never
+       waits on a peer.  Keep the fast kernel across ranks only while the waiters leave at least one slot
+       per SM free (512^2 planes: 256 waiters, 444 slots); larger planes (ny * nz >~ 3e5 nodes) use the
+       generic kernel, whose grid is one resident wave. */
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ar3d_march<true>, kT, 0);
+    if (occ < 1) occ = 1;
+    if ((int64_t)p->tiles + p->sms > (int64_t)p->sms * occ) p->fast = false;
+  }
   {
     /* generic kernel: persistent grid of at most one resident wave (its CTAs wait on peers) */
     int occ = 1;
