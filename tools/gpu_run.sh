@@ -17,7 +17,7 @@ case "$what" in
   bench)   timeout 1500 python bench.py "$@" > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"; tail -c 1800 gpurun_out/${tag}_bench.json; tail -5 gpurun_out/${tag}_bench.err ;;
   mb)      timeout 600 build/mb_reduce2 "$@" > gpurun_out/${tag}_mb_reduce2.txt 2>&1; echo "mb rc=$?"; tail -3 gpurun_out/${tag}_mb_reduce2.txt ;;
   launches) timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py "$@" > gpurun_out/${tag}_launches_bench.log 2>&1; echo "ncu rc=$?"; wc -l gpurun_out/${tag}_launches.csv ;;
-  full)    timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_map|k_reduce|k_lincomb|k_scaleadd' -s 11 -c 11 -o gpurun_out/${tag}_full -f python tools/profile_kernels.py "$@" > gpurun_out/${tag}_full.log 2>&1; echo "ncu rc=$?"; ls -la gpurun_out/${tag}_full.ncu-rep ;;
+  full)    timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_map|k_reduce|k_lincomb|k_scaleadd' -s 14 -c 14 -o gpurun_out/${tag}_full -f python tools/profile_kernels.py "$@" > gpurun_out/${tag}_full.log 2>&1; echo "ncu rc=$?"; ls -la gpurun_out/${tag}_full.ncu-rep ;;
   cmd)     bash -c "$*" ;;
   *) echo "unknown: $what"; exit 2 ;;
 esac

@@ -1,7 +1,8 @@
 """Launch each representative kernel a few times (target for ncu captures).
    ncu --set full --clock-control none --import-source on -k regex:'k_map|k_reduce|k_lincomb|k_scaleadd' \
-       -s 11 -c 11 -o gpurun_out/prof python tools/profile_kernels.py --n 24   (second repetition)"""
+       -s 14 -c 14 -o gpurun_out/prof python tools/profile_kernels.py --n 24   (second repetition)"""
 import argparse
+import ctypes as C
 import sys
 from pathlib import Path
 
@@ -30,5 +31,9 @@ for _ in range(a.reps):
     nv.N_VWrmsNormVectorArray(V[:8], V[11:19])               # k_reduce_multi<4,1>
     nv.N_VLinearCombinationSqNorm([1.0] + c[:5], [V[20]] + V[:5], V[20])   # k_lincomb_sqnorm<4> (fused CGS step, k = 5)
     nv.N_VDotProdMulti(V[21], V[:20] + [V[21]])              # k_reduce_multi<4,0,24,1>: 21-wide (GMRES maxl = 20)
+    r = C.c_double()
+    ctx.lib.b200vec_axpy_dot(ctx.h, -0.37, V[22].ptr, V[23].ptr, V[24].ptr, n, C.byref(r))   # k_reduce<4,2,RAxpyDot>
+    ctx.lib.b200vec_ewt_set(ctx.h, 1e-5, 1e-10, None, V[22].ptr, V[25].ptr, n, C.byref(r))   # k_reduce<4,2,REwt<false>>
+    nv.N_VInvTest(V[22], V[25])                              # k_reduce<4,4,RInvTest>, one tile per CTA
 torch.cuda.synchronize()
 print("done")
