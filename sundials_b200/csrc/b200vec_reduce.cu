@@ -213,7 +213,7 @@ struct REwt
   static constexpr int NIN = VEC ? 2 : 1;
   static constexpr bool HAS_OUT = true;
   static constexpr bool NAN_HEAD = false;
-  static constexpr int MAXU = 2;
+  static constexpr int MAXU = VEC ? 2 : 4; /* measured: 43.2 vs 46.0 us (scalar atol), 60.3 vs 71.2 us (vector atol) at 2^24 */
   double rtol, atol;
   __device__ double term(double y, double av, double, double& outv, bool& store) const
   {
