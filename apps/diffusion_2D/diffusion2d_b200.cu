@@ -324,11 +324,11 @@ __global__ void __launch_bounds__(kThreads, MINB) k_diffusion_rhs(const __grid_c
  * finished afterwards by the register path, exactly as in k_diffusion_rhs.
  * ------------------------------------------------------------------------------------ */
 constexpr int kTX        = kThreads * 4; /* x-points per CTA tile */
-constexpr int kStages    = 12;
+constexpr int kStagesMax = 12; /* the mbarrier block at the head of shared memory is sized for this */
 constexpr int kRowDbl    = kTX + 4; /* a stage holds x0-2 .. x0+kTX+1 (16-byte aligned both ends) */
 constexpr int kTmaRows   = 256;     /* max rows per CTA (y factors staged in shared memory) */
 constexpr int kTmaThreads = kThreads + 32;
-constexpr size_t kTmaSmem = 256 + (size_t)kStages * kRowDbl * sizeof(double);
+constexpr size_t tma_smem(int stages) { return 256 + (size_t)stages * kRowDbl * sizeof(double); }
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
@@ -376,13 +376,15 @@ __device__ __forceinline__ void lds4(const double* p, double (&v)[4])
   asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "r"(a + 16) : "memory");
 }
 
-__global__ void __launch_bounds__(kTmaThreads, 2) k_diffusion_rhs_tma(const __grid_constant__ RhsArgs a, int R)
+template <int kStages, int MINB>
+__global__ void __launch_bounds__(kTmaThreads, MINB) k_diffusion_rhs_tma(const __grid_constant__ RhsArgs a, int R)
 {
+  static_assert(kStages <= kStagesMax, "mbarrier block");
   constexpr int W = 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_sy[kTmaRows], s_dy[kTmaRows];
   const uint32_t bar_full  = smem_addr(smem_raw);                 /* kStages x 8 B */
-  const uint32_t bar_empty = bar_full + 8 * kStages;              /* kStages x 8 B */
+  const uint32_t bar_empty = bar_full + 8 * kStagesMax;           /* kStages x 8 B */
   double* const ring       = (double*)(smem_raw + 256);
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -609,6 +611,8 @@ struct b200_diffusion2d_plan_s
 {
   rhs_kernel_t kernel = nullptr; /* register-march kernel (any nx, any alignment) */
   bool use_tma        = false;   /* TMA ring kernel when nx % 4 == 0 and u is 16-byte aligned */
+  rhs_kernel_t tma_kernel = nullptr; /* the ring instantiation in use and its dynamic shared memory */
+  size_t tma_smem_bytes   = 0;
   b200vec_ctx ctx     = nullptr;
   b200_diffusion2d_opts o;
   int rank = 0, np = 1;
@@ -715,14 +719,24 @@ int b200_diffusion2d_plan_create(b200vec_ctx ctx, const b200_diffusion2d_opts* o
     p->use_tma       = (p->W == 4) && (!want || !strcmp(want, "tma"));
     if (p->use_tma)
     {
-      if (cudaFuncSetAttribute(k_diffusion_rhs_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem) !=
+      /* ring geometry: stages x resident CTAs per SM (B200_DIFFUSION_TMA = "12x2" | "8x3" | "6x3"; tuning) */
+      struct { const char* name; rhs_kernel_t k; int stages; } rings[] = {
+        {"12x2", k_diffusion_rhs_tma<12, 2>, 12}, {"8x3", k_diffusion_rhs_tma<8, 3>, 8}, {"6x3", k_diffusion_rhs_tma<6, 3>, 6},
+        {"8x2", k_diffusion_rhs_tma<8, 2>, 8}};
+      int pick = 0;
+      if (const char* r = getenv("B200_DIFFUSION_TMA"))
+        for (int i = 0; i < 4; i++)
+          if (!strcmp(rings[i].name, r)) pick = i;
+      p->tma_kernel     = rings[pick].k;
+      p->tma_smem_bytes = tma_smem(rings[pick].stages);
+      if (cudaFuncSetAttribute(p->tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->tma_smem_bytes) !=
           cudaSuccess)
       {
         cudaGetLastError();
         p->use_tma = false;
       }
     }
-    if (p->use_tma) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_diffusion_rhs_tma, kTmaThreads, kTmaSmem);
+    if (p->use_tma) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->tma_kernel, kTmaThreads, p->tma_smem_bytes);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->kernel, kThreads, 0);
     if (occ < 1) occ = 1;
     int64_t R = p->o.rows_per_cta;
@@ -850,8 +864,8 @@ int b200_diffusion2d_rhs(b200_diffusion2d_plan p, double t, const double* u, dou
   if (p->use_tma && ((uintptr_t)u % 16 == 0) && ((uintptr_t)f % 32 == 0))
   {
     cfg.blockDim         = dim3(kTmaThreads);
-    cfg.dynamicSmemBytes = kTmaSmem;
-    e                    = cudaLaunchKernelEx(&cfg, k_diffusion_rhs_tma, a, R);
+    cfg.dynamicSmemBytes = p->tma_smem_bytes;
+    e                    = cudaLaunchKernelEx(&cfg, p->tma_kernel, a, R);
   }
   else e = cudaLaunchKernelEx(&cfg, p->kernel, a, R);
   if (e != cudaSuccess)
