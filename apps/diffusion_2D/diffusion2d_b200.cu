@@ -166,6 +166,37 @@ __device__ __forceinline__ void stencil_store(const RhsArgs& a, int64_t j, int64
   st_row<W>(a.f + j * a.nx + x0, r);
 }
 
+/* the same row for the TMA sweep: the x-interior / y-boundary tests are loop invariants there, so
+   they arrive as a bit mask (bit k = point k is an interior node) and the row is computed without
+   branches; a masked-off point stores 0 exactly like stencil_store.  Same operation order. */
+template <int W>
+__device__ __forceinline__ void stencil_store_masked(const RhsArgs& a, double* out, const double (&s)[W],
+                                                     const double (&c)[W], const double (&n)[W], double w, double e,
+                                                     double sy, double dy, const double (&tdcx)[W],
+                                                     const double (&tssx)[W], unsigned mask)
+{
+  double r[W];
+#pragma unroll
+  for (int k = 0; k < W; k++)
+  {
+    const double uw = (k == 0) ? w : c[k - 1];
+    const double ue = (k == W - 1) ? e : c[k + 1];
+    r[k]            = a.cc * c[k] + a.cx * (uw + ue) + a.cy * (s[k] + n[k]);
+  }
+  if (a.forcing)
+  {
+#pragma unroll
+    for (int k = 0; k < W; k++)
+    {
+      const double b = (-2.0 * PI_) * tssx[k] * sy * a.stct - tdcx[k] * sy * a.c2t - dy * tssx[k] * a.c2t;
+      r[k] += b;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < W; k++) r[k] = ((mask >> k) & 1u) ? r[k] : 0.0;
+  st_row<W>(out, r);
+}
+
 /* register path: west / east neighbours by warp shuffle, warp edges prefetched */
 template <int W>
 __device__ __forceinline__ void compute_row(const RhsArgs& a, int64_t j, int64_t x0, bool act, const double (&s)[W],
@@ -523,27 +554,48 @@ __global__ void __launch_bounds__(kTmaThreads, MINB) k_diffusion_rhs_tma(const _
       }
       const double* pc = next_row();
       lds4(pc + px, c);
-      for (int64_t j = m0; j < m1; j++)
-      {
+      /* loop invariants of the row sweep: which of the thread's W points are x-interior, the two
+         (CTA-relative) rows that lie on the global y boundary, and a running output pointer */
+      unsigned inmask = 0;
+#pragma unroll
+      for (int k = 0; k < W; k++)
+        if (act && x0 + k > 0 && x0 + k < a.nx - 1) inmask |= 1u << k;
+      const int64_t g0 = a.js + jb; /* global index of the CTA's first row */
+      const int yb0    = (g0 <= 0 && -g0 < kTmaRows) ? (int)(-g0) : -1;
+      const int yb1    = (a.ny - 1 - g0 >= 0 && a.ny - 1 - g0 < kTmaRows) ? (int)(a.ny - 1 - g0) : -1;
+      int jr           = (int)(m0 - jb);
+      const int jr_end = (int)(m1 - jb), jr_hi = (int)(hi - jb);
+      double* fp       = a.f + m0 * a.nx + xo;
+      /* one row with the roles of the three register rows given by the caller, so that the sweep
+         below rotates names instead of moving 8 doubles per row */
+      auto row = [&](const double(&S)[W], const double(&C)[W], double(&N)[W]) {
         const double* pn = pc;
-        if (j + 1 <= hi)
+        if (jr < jr_hi)
         {
           pn = next_row();
-          lds4(pn + px, n);
+          lds4(pn + px, N);
         }
         if (act)
         {
           const double w = pc[px - 1], e = pc[px + W];
-          stencil_store<W>(a, j, x0, s, c, n, w, e, s_sy[j - jb], s_dy[j - jb], tdcx, tssx);
+          const unsigned m = (jr == yb0 || jr == yb1) ? 0u : inmask;
+          stencil_store_masked<W>(a, fp, S, C, N, w, e, s_sy[jr], s_dy[jr], tdcx, tssx, m);
         }
-        release(); /* row j served as centre: free its stage */
-#pragma unroll
-        for (int k = 0; k < W; k++)
-        {
-          s[k] = c[k];
-          c[k] = n[k];
-        }
+        release(); /* the row served as centre: free its stage */
+        fp += a.nx;
         pc = pn;
+        jr++;
+      };
+      while (jr + 3 <= jr_end)
+      {
+        row(s, c, n);
+        row(c, n, s);
+        row(n, s, c);
+      }
+      if (jr < jr_end)
+      {
+        row(s, c, n);
+        if (jr < jr_end) row(c, n, s);
       }
     }
   }
