@@ -166,6 +166,30 @@ int b200vec_min_quotient(b200vec_ctx ctx, const double* num, const double* denom
 int b200vec_ewt_set(b200vec_ctx ctx, double rtol, double atol, const double* atol_vec, const double* y,
                     double* w, int64_t n, double* min_denominator_host);
 
+/* ---- integrator-level fused streaming kernels: the bodies of libsundials_cvode_fused_b200.so
+ * (include/cvode_fused_b200.h).  One launch each, no host wait; results bit-identical to the N_V* op
+ * sequences of src/cvode/cvode_fused_stubs.c on nvector_serial (the line ranges below), which the
+ * reference's CUDA kernels (src/cvode/cvode_fused_gpu.cpp) fuse for nvector_cuda.  Outputs may alias
+ * inputs as the integrators do (M, y, tempv are updated in place). */
+/* tempv = rtol |y| + atol_i, weight = 1 / tempv (stubs:38-72).  weight == NULL: tempv only.  atol_vec == NULL:
+ * scalar atol.  24 B/elt (32 with a vector atol) instead of 64 (72). */
+int b200vec_cv_ewt(b200vec_ctx ctx, double rtol, double atol, const double* atol_vec, const double* y, double* tempv,
+                   double* weight, int64_t n);
+/* tmp = mm (y - 0.1 a c / ewt), a_i = 1 where |c_i| >= 1.5 (stubs:80-89): 40 B/elt instead of 112 */
+int b200vec_cv_constraints(b200vec_ctx ctx, const double* c, const double* ewt, const double* y, const double* mm,
+                           double* tmp, int64_t n);
+/* res = rl1 zn1 + ycor + ngamma ftemp (stubs:97-104): 32 B/elt instead of 48 */
+int b200vec_cv_nls_resid(b200vec_ctx ctx, double rl1, double ngamma, const double* zn1, const double* ycor,
+                         const double* ftemp, double* res, int64_t n);
+/* ftemp = h fpred - zn1, y = r ftemp + ypred (stubs:112-119): 40 B/elt instead of 48 */
+int b200vec_cv_diag_form_y(b200vec_ctx ctx, double h, double r, const double* fpred, const double* zn1,
+                           const double* ypred, double* ftemp, double* y, int64_t n);
+/* the 11-op construction of M = I - gamma J with the round-off guard (stubs:128-147): 64 B/elt instead of 264 */
+int b200vec_cv_diag_build_m(b200vec_ctx ctx, double uround, double h, const double* ftemp, const double* fpred,
+                            const double* ewt, double* bit, double* bitcomp, double* y, double* M, int64_t n);
+/* M = 1 + r (1/M - 1) (stubs:154-161): 16 B/elt instead of 64 */
+int b200vec_cv_diag_update_m(b200vec_ctx ctx, double r, double* M, int64_t n);
+
 /* z <- a x + z (serial's Vaxpy form, serial:1734) and result = sum_i w_i z_i of the UPDATED z, one
  * pass: a modified Gram-Schmidt step -- N_VLinearSum(1, v_k, -h_i, v_i, v_k) + N_VDotProd(v_{i+1}, v_k),
  * src/sundials/sundials_iterative.c:62-67 -- at 32 B/elt instead of 24 + 16.  w may alias x. */

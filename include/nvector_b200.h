@@ -95,6 +95,9 @@ SUNErrCode N_VSetStream_B200(N_Vector v, void* stream);
 
 /* ---- ops-table entries (also callable directly, like N_V*_Serial) ---- */
 N_Vector_ID N_VGetVectorID_B200(N_Vector v);
+/* the ID v and its future clones report: SUNDIALS_NVEC_CUSTOM (default) or SUNDIALS_NVEC_CUDA, which the
+   reference demands before it enables CVODE's fused kernels (cvode_io.c:1022-1029; include/cvode_fused_b200.h) */
+SUNErrCode N_VSetVectorID_B200(N_Vector v, N_Vector_ID id);
 N_Vector N_VCloneEmpty_B200(N_Vector w);
 N_Vector N_VClone_B200(N_Vector w);
 void N_VDestroy_B200(N_Vector v);

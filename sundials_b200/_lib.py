@@ -80,6 +80,12 @@ _SIGS = {
     "b200vec_min_quotient": (_I, [ctx_t, _V, _V, _L, c_double_p]),
     "b200vec_ewt_set": (_I, [ctx_t, _D, _D, _V, _V, _V, _L, c_double_p]),
     "b200vec_axpy_dot": (_I, [ctx_t, _D, _V, _V, _V, _L, c_double_p]),
+    "b200vec_cv_ewt": (_I, [ctx_t, _D, _D, _V, _V, _V, _V, _L]),
+    "b200vec_cv_constraints": (_I, [ctx_t, _V, _V, _V, _V, _V, _L]),
+    "b200vec_cv_nls_resid": (_I, [ctx_t, _D, _D, _V, _V, _V, _V, _L]),
+    "b200vec_cv_diag_form_y": (_I, [ctx_t, _D, _D, _V, _V, _V, _V, _V, _L]),
+    "b200vec_cv_diag_build_m": (_I, [ctx_t, _D, _D, _V, _V, _V, _V, _V, _V, _V, _L]),
+    "b200vec_cv_diag_update_m": (_I, [ctx_t, _D, _V, _L]),
     "b200vec_mgs_sweep": (_I, [ctx_t, _I, _V, c_ptr_table, _L, c_double_p, c_double_p]),
     "b200vec_cgs_step": (_I, [ctx_t, _I, _V, c_ptr_table, c_ptr_table, _V, _L, c_double_p, c_double_p]),
     "b200vec_result_device": (_V, [ctx_t]),

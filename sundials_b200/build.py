@@ -31,11 +31,15 @@ OBJ = ROOT / "build" / "obj"
 LIBDIR = ROOT / "sundials_b200" / "lib"
 LIB = LIBDIR / "libsundials_nvecb200.so"
 
-CU_SOURCES = ["b200vec_ctx.cu", "b200vec_stream.cu", "b200vec_reduce.cu", "b200vec_fused.cu", "b200vec_comm.cu"]
+CU_SOURCES = ["b200vec_ctx.cu", "b200vec_stream.cu", "b200vec_reduce.cu", "b200vec_fused.cu", "b200vec_cvfused.cu",
+              "b200vec_comm.cu"]
 C_SOURCES = ["nvector_b200.c", "sundials_iterative_b200.c"]
 # separate tiny library: symbol interposition of SUNClassicalGS (see gs_interpose.c)
 GS_LIB = LIBDIR / "libsundials_b200gs.so"
 GS_SOURCES = ["gs_interpose.c"]
+# separate library: CVODE's fused-kernel plugin boundary (takes the place of libsundials_cvode_fused_cuda)
+CVF_LIB = LIBDIR / "libsundials_cvode_fused_b200.so"
+CVF_SOURCES = ["cvode_fused_b200.c"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -83,10 +87,10 @@ def _run(cmd: list[str], verbose: bool) -> str:
 def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     headers = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list(INC.glob("*.h"))
-    sources = [CSRC / s for s in CU_SOURCES + C_SOURCES + GS_SOURCES]
+    sources = [CSRC / s for s in CU_SOURCES + C_SOURCES + GS_SOURCES + CVF_SOURCES]
     stamp = LIBDIR / ".build_digest"
     digest = _digest(headers + sources, " ".join(NVCC_FLAGS))
-    if not force and LIB.exists() and GS_LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+    if not force and LIB.exists() and GS_LIB.exists() and CVF_LIB.exists() and stamp.exists() and stamp.read_text() == digest:
         return LIB
     if not Path(nvcc).exists() or not have_sundials_headers():
         if LIB.exists():
@@ -118,9 +122,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     # host link only (no relocatable device code): keeps the library pure sm_100a
     _run([gxx, "-shared", "-o", str(LIB), *objs, f"-L{cuda_lib}", "-lcudart_static", "-Wl,--no-undefined", "-ldl",
           "-lm", "-lpthread", "-lrt"], verbose)
-    # the interposer resolves SUNClassicalGS_B200 / N_VGetVectorID_B200 from the main library
+    # the interposer resolves SUNClassicalGS_B200 / N_VCloneEmpty_B200 from the main library
     _run([GCC, "-O2", "-std=gnu99", "-fPIC", "-shared", "-Wall", f"-I{INC}", *sun_inc, "-o", str(GS_LIB),
           *[str(CSRC / s) for s in GS_SOURCES], f"-L{LIBDIR}", "-lsundials_nvecb200", "-Wl,-rpath,$ORIGIN", "-ldl"],
+         verbose)
+    # the fused-kernel plugin: seven reference symbols over the b200vec_cv_* kernels of the main library
+    _run([GCC, "-O2", "-std=gnu99", "-fPIC", "-shared", "-Wall", f"-I{INC}", *sun_inc, "-o", str(CVF_LIB),
+          *[str(CSRC / s) for s in CVF_SOURCES], f"-L{LIBDIR}", "-lsundials_nvecb200", "-Wl,-rpath,$ORIGIN"],
          verbose)
     stamp.write_text(digest)
     return LIB

@@ -29,7 +29,7 @@ typedef SUNErrCode (*cgs_fn)(N_Vector*, sunrealtype**, int, int, sunrealtype*, s
 SUNErrCode SUNClassicalGS(N_Vector* v, sunrealtype** h, int k, int p, sunrealtype* new_vk_norm, sunrealtype* stemp,
                           N_Vector* vtemp)
 {
-  if (v && v[0] && v[0]->ops && v[0]->ops->nvgetvectorid == N_VGetVectorID_B200)
+  if (v && v[0] && v[0]->ops && v[0]->ops->nvcloneempty == N_VCloneEmpty_B200)
     return SUNClassicalGS_B200(v, h, k, p, new_vk_norm, stemp, vtemp);
   static cgs_fn next = NULL;
   if (!next)
@@ -48,7 +48,7 @@ typedef SUNErrCode (*mgs_fn)(N_Vector*, sunrealtype**, int, int, sunrealtype*);
 
 SUNErrCode SUNModifiedGS(N_Vector* v, sunrealtype** h, int k, int p, sunrealtype* new_vk_norm)
 {
-  if (v && v[0] && v[0]->ops && v[0]->ops->nvgetvectorid == N_VGetVectorID_B200)
+  if (v && v[0] && v[0]->ops && v[0]->ops->nvcloneempty == N_VCloneEmpty_B200)
     return SUNModifiedGS_B200(v, h, k, p, new_vk_norm);
   static mgs_fn next = NULL;
   if (!next)

@@ -331,6 +331,24 @@ N_Vector_ID N_VGetVectorID_B200(N_Vector v)
   return SUNDIALS_NVEC_CUSTOM;
 }
 
+/* NVECTOR_B200 answering as the vector it replaces: the one place the reference keys on the CUDA ID is the
+   gate of CVodeSetUseIntegratorFusedKernels (src/cvode/cvode_io.c:1022-1029).  The ID lives in the ops
+   table, which clones copy (N_VCloneEmpty_B200), so the template vector's choice propagates. */
+static N_Vector_ID getvectorid_as_cuda(N_Vector v)
+{
+  (void)v;
+  return SUNDIALS_NVEC_CUDA;
+}
+
+SUNErrCode N_VSetVectorID_B200(N_Vector v, N_Vector_ID id)
+{
+  if (!v || !v->ops) return SUN_ERR_ARG_CORRUPT;
+  if (id == SUNDIALS_NVEC_CUSTOM) v->ops->nvgetvectorid = N_VGetVectorID_B200;
+  else if (id == SUNDIALS_NVEC_CUDA) v->ops->nvgetvectorid = getvectorid_as_cuda;
+  else return SUN_ERR_ARG_OUTOFRANGE;
+  return SUN_SUCCESS;
+}
+
 sunindextype N_VGetLength_B200(N_Vector v) { return NVC(v)->global_length; }
 sunindextype N_VGetLocalLength_B200(N_Vector v) { return NVC(v)->length; }
 b200vec_ctx N_VGetCtx_B200(N_Vector v) { return NCTX(v); }

@@ -14,11 +14,21 @@
 
 #include "nvector_b200.h"
 
-#define N_VNew_Cuda                   N_VNew_B200
-#define N_VNewManaged_Cuda            N_VNewManaged_B200
-#define N_VNewEmpty_Cuda              N_VNewEmpty_B200
-#define N_VMake_Cuda                  N_VMake_B200
-#define N_VMakeManaged_Cuda           N_VMakeManaged_B200
+/* the constructors also make the vector answer N_VGetVectorID with SUNDIALS_NVEC_CUDA, as the vector it
+   stands in for does (nvector_cuda.h:114): CVodeSetUseIntegratorFusedKernels tests it (cvode_io.c:1022-1029) */
+static inline N_Vector b200_shim_as_cuda(N_Vector v)
+{
+  if (v) N_VSetVectorID_B200(v, SUNDIALS_NVEC_CUDA);
+  return v;
+}
+#define N_VNew_Cuda(n, ctx)              b200_shim_as_cuda(N_VNew_B200(n, ctx))
+#define N_VNewManaged_Cuda(n, ctx)       b200_shim_as_cuda(N_VNewManaged_B200(n, ctx))
+#define N_VNewEmpty_Cuda(ctx)            b200_shim_as_cuda(N_VNewEmpty_B200(ctx))
+#define N_VMake_Cuda(n, h, d, ctx)       b200_shim_as_cuda(N_VMake_B200(n, h, d, ctx))
+#define N_VMakeManaged_Cuda(n, p, ctx)   b200_shim_as_cuda(N_VMakeManaged_B200(n, p, ctx))
+#define N_VClone_Cuda                 N_VClone_B200
+#define N_VCloneEmpty_Cuda            N_VCloneEmpty_B200
+#define N_VDestroy_Cuda               N_VDestroy_B200
 #define N_VGetHostArrayPointer_Cuda   N_VGetHostArrayPointer_B200
 #define N_VGetDeviceArrayPointer_Cuda N_VGetDeviceArrayPointer_B200
 #define N_VCopyToDevice_Cuda          N_VCopyToDevice_B200

@@ -120,6 +120,46 @@ def test_reference_cuda_example_with_device_rhs_kernels():
     assert "nst     =   143" in r.stdout and "nli     =   225" in r.stdout
 
 
+def _diag(toltype, fused):
+    import os
+
+    env = dict(os.environ, B200CVF_REPORT="1", B200VEC_REPORT="1")
+    r = subprocess.run([str(BINB / "cvAdvDiff_diag_cuda_b200"), str(toltype), str(fused)], capture_output=True, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SUNDIALS_ERROR" not in r.stderr and "not supported" not in r.stderr, r.stderr[-1500:]
+    calls = {x.split("] ")[1].split(" calls")[0]: int(x.rsplit(":", 1)[1]) for x in r.stderr.splitlines() if " calls: " in x}
+    launches = sum(json.loads(x.split("report: ")[1])["kernel_launches"] for x in r.stderr.splitlines() if "report: " in x)
+    return r.stdout, calls, launches
+
+
+@pytest.mark.parametrize("toltype", [0, 1])
+def test_reference_cuda_diag_example_with_integrator_fused_kernels(toltype):
+    """examples/cvode/cuda/cvAdvDiff_diag_cuda.cu, UNMODIFIED, on the reference's CVODE built with its own
+    SUNDIALS_BUILD_PACKAGE_FUSED_KERNELS switch and libsundials_cvode_fused_b200.so in the place of
+    libsundials_cvode_fused_cuda: CVodeSetUseIntegratorFusedKernels accepts the vector, CVODE comes through
+    the plugin (error weights, nonlinear residual, CVDiag setup / solve), and -- because each fused kernel
+    repeats the unfused op sequence bit for bit -- the run prints exactly what the unfused run prints, with
+    fewer kernel launches.  (The reference's own CUDA fused kernels change every counter: nst 1448 -> 1465.)"""
+    off, calls_off, launches_off = _diag(toltype, 0)
+    on, calls_on, launches_on = _diag(toltype, 1)
+    assert " Using fused CVODE kernels \n" in on
+    assert on.replace(" Using fused CVODE kernels \n", "") == off, _first_diff(on, off)
+    assert all(v == 0 for v in calls_off.values()), calls_off
+    ewt = "cvEwtSetSV_fused" if toltype else "cvEwtSetSS_fused"
+    for f in (ewt, "cvNlsResid_fused", "cvDiagSetup_formY", "cvDiagSetup_buildM", "cvDiagSolve_updateM"):
+        assert calls_on[f] > 0, calls_on
+    assert launches_on < 0.8 * launches_off, (launches_on, launches_off)
+
+
+def test_reference_cuda_diag_example_unfused_against_the_reference_output():
+    """the same program with the fused kernels off against the output the reference ships for it on
+    nvector_cuda (cvAdvDiff_diag_cuda_0_0.out): every printed norm and every counter"""
+    out, _, _ = _diag(0, 0)
+    want = (GOLD / "cvAdvDiff_diag_cuda_0_0.refcuda.out").read_text()
+    assert out == want, _first_diff(out, want)
+
+
 @pytest.mark.parametrize("tag", sorted(MANIFEST))
 def test_reference_program_output_identical_to_serial_golden(tag):
     e = MANIFEST[tag]
