@@ -172,7 +172,7 @@ int b200vec_ewt_set(b200vec_ctx ctx, double rtol, double atol, const double* ato
  * reference's CUDA kernels (src/cvode/cvode_fused_gpu.cpp) fuse for nvector_cuda.  Outputs may alias
  * inputs as the integrators do (M, y, tempv are updated in place). */
 /* tempv = rtol |y| + atol_i, weight = 1 / tempv (stubs:38-72).  weight == NULL: tempv only.  atol_vec == NULL:
- * scalar atol.  24 B/elt (32 with a vector atol) instead of 64 (72). */
+ * scalar atol.  24 B/elt (32 with a vector atol) instead of 64 (56). */
 int b200vec_cv_ewt(b200vec_ctx ctx, double rtol, double atol, const double* atol_vec, const double* y, double* tempv,
                    double* weight, int64_t n);
 /* tmp = mm (y - 0.1 a c / ewt), a_i = 1 where |c_i| >= 1.5 (stubs:80-89): 40 B/elt instead of 112 */
@@ -184,7 +184,7 @@ int b200vec_cv_nls_resid(b200vec_ctx ctx, double rl1, double ngamma, const doubl
 /* ftemp = h fpred - zn1, y = r ftemp + ypred (stubs:112-119): 40 B/elt instead of 48 */
 int b200vec_cv_diag_form_y(b200vec_ctx ctx, double h, double r, const double* fpred, const double* zn1,
                            const double* ypred, double* ftemp, double* y, int64_t n);
-/* the 11-op construction of M = I - gamma J with the round-off guard (stubs:128-147): 64 B/elt instead of 264 */
+/* the 10-op construction of M = I - gamma J with the round-off guard (stubs:128-147): 64 B/elt instead of 224 */
 int b200vec_cv_diag_build_m(b200vec_ctx ctx, double uround, double h, const double* ftemp, const double* fpred,
                             const double* ewt, double* bit, double* bitcomp, double* y, double* M, int64_t n);
 /* M = 1 + r (1/M - 1) (stubs:154-161): 16 B/elt instead of 64 */

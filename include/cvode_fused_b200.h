@@ -12,7 +12,7 @@
  *   cvCheckConstraints_fused    cvode.c:3182, cvode_constraints.c:61  5     :80-89
  *   cvNlsResid_fused            cvode_nls.c:388 (cvNlsResidual)       2     :97-104
  *   cvDiagSetup_formY           cvode_diag.c:344                      2     :112-119
- *   cvDiagSetup_buildM          cvode_diag.c:373                      11    :128-147
+ *   cvDiagSetup_buildM          cvode_diag.c:373                      10    :128-147
  *   cvDiagSolve_updateM         cvode_diag.c:434                      4     :154-161
  *
  * Each is ONE kernel (b200vec_cv_*, include/b200vec.h) whose element-wise arithmetic is the stubs' op

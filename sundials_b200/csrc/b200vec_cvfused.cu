@@ -3,7 +3,7 @@
  * The reference has a second plugin boundary next to the vector's ops table: libsundials_cvode links one
  * of libsundials_cvode_fused_{stubs,cuda,hip} (src/cvode/CMakeLists.txt:43-75), which all export the same
  * seven C functions (src/cvode/cvode_impl.h:639-672).  The stubs spell each of them as a sequence of
- * N_V* calls (src/cvode/cvode_fused_stubs.c:38-162: 2-11 ops, 5-33 array passes), the CUDA library as one
+ * N_V* calls (src/cvode/cvode_fused_stubs.c:38-162: 2-10 ops, 6-28 array passes), the CUDA library as one
  * kernel each (src/cvode/cvode_fused_gpu.cpp:62-420).  This file holds the sm_100a kernels behind
  * libsundials_cvode_fused_b200.so (cvode_fused_b200.c): one launch per function, every operand read
  * once, every result written once, and -- unlike the reference's CUDA kernels, which are compiled with
@@ -94,7 +94,7 @@ struct FCvDiagBuildM
   int form;
   __device__ void operator()(const double* in, double* out, int) const
   {
-    const double fract = 0.1; /* FRACT of the stubs (cvode_diag_impl.h) */
+    const double fract = 0.1; /* FRACT of the stubs (cvode_fused_stubs.c:28) */
     const double ft    = in[0];
     double M           = in[3] - in[1]; /* N_VLinearSum(1, M, -1, fpred, M): M -= fpred */
     if (form == 1) M = fract * (ft + M);
@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(kBlock) k_mapn(F f, const __grid_constant__ Ma
   }
 }
 
-/* widest access every operand's alignment allows; unroll 2 for <= 3 arrays in flight, 1 above (the
-   same bytes in flight per thread as k_map's W = 4, U = 4 with two operands) */
+/* widest access every operand's alignment allows; two tiles in flight per thread with one or two inputs,
+   one with three or four (64-128 B of loads in flight per thread, as k_map's two operands at U = 2) */
 template <int NIN, int NOUT, class F>
 static int launch_mapn(b200vec_ctx ctx, const char* name, F f, const MapnPtrs& p, int64_t n)
 {

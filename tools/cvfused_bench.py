@@ -30,11 +30,11 @@ UR = float(np.finfo(np.float64).eps)
 # name -> (vectors, arrays moved per element by the fused kernel, arrays moved by the op sequence, call)
 CASES = {
     "cvEwtSetSS_fused": (3, 3, 8, lambda L, v: L.cvEwtSetSS_fused(0, 1e-4, 1e-6, v[0], v[1], v[2])),
-    "cvEwtSetSV_fused": (4, 4, 9, lambda L, v: L.cvEwtSetSV_fused(0, 1e-4, v[3], v[0], v[1], v[2])),
+    "cvEwtSetSV_fused": (4, 4, 7, lambda L, v: L.cvEwtSetSV_fused(0, 1e-4, v[3], v[0], v[1], v[2])),
     "cvCheckConstraints_fused": (5, 5, 14, lambda L, v: L.cvCheckConstraints_fused(v[0], v[1], v[2], v[3], v[4])),
     "cvNlsResid_fused": (4, 4, 6, lambda L, v: L.cvNlsResid_fused(0.37, -0.013, v[0], v[1], v[2], v[3])),
     "cvDiagSetup_formY": (5, 5, 6, lambda L, v: L.cvDiagSetup_formY(0.02, 0.05, v[0], v[1], v[2], v[3], v[4])),
-    "cvDiagSetup_buildM": (7, 8, 33, lambda L, v: L.cvDiagSetup_buildM(0.1, UR, 0.02, v[0], v[1], v[2], v[3], v[4], v[5], v[6])),
+    "cvDiagSetup_buildM": (7, 8, 28, lambda L, v: L.cvDiagSetup_buildM(0.1, UR, 0.02, v[0], v[1], v[2], v[3], v[4], v[5], v[6])),
     "cvDiagSolve_updateM": (1, 2, 8, lambda L, v: L.cvDiagSolve_updateM(1.0, v[0])),  # r = 1: M keeps its magnitude
 }
 
