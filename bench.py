@@ -1063,6 +1063,18 @@ def b200_arm(args):
         except Exception as e:
             gs = {"unavailable": f"{type(e).__name__}: {e}"}
 
+    # ---- CVODE's fused-kernel plugin (SURVEY f-N3): libsundials_cvode_fused_b200.so beside the unfused path (the
+    # reference's stubs library driving this vector through the ops table), N = 1 only
+    cvf = None
+    if world == 1 and not args.no_cvfused:
+        try:
+            sys.path.insert(0, str(ROOT / "tools"))
+            import cvfused_bench
+
+            cvf = cvfused_bench.run(args.log2n, reps=10, with_ref_cuda=False)
+        except Exception as e:
+            cvf = {"unavailable": f"{type(e).__name__}: {e}"}
+
     # ---- length sweep (BASELINE config 3), bounded in the default run; collective
     sweep = None
     if not args.no_sweep:
@@ -1143,6 +1155,12 @@ def b200_arm(args):
                                                            "nni": fp["nls_iters"]}
     if gs and "b200" in gs:
         legs["gram_schmidt"] = {k: gs["b200"][k]["cycle_frac_of_peak"] for k in gs["b200"]}
+    if cvf is not None and "functions" in cvf:
+        short = {"cvEwtSetSS_fused": "ewtSS", "cvEwtSetSV_fused": "ewtSV", "cvCheckConstraints_fused": "constr",
+                 "cvNlsResid_fused": "nlsres", "cvDiagSetup_formY": "formY", "cvDiagSetup_buildM": "buildM",
+                 "cvDiagSolve_updateM": "updM"}
+        # [fraction of the HBM peak, speed-up over the unfused op sequence on the same vector]
+        legs["cvode_fused"] = {short[k]: [v["fused_frac_of_peak"], v["speedup_vs_unfused"]] for k, v in cvf["functions"].items()}
     if cvd and "b200_pinned_s" in cvd:
         legs["cvDiurnal_kry"] = {"b200_s": cvd["b200_pinned_s"], "serial_s": cvd.get("serial_1core_s"),
                                  "identical": cvd.get("stdout_identical_to_serial_golden")}
@@ -1183,6 +1201,7 @@ def b200_arm(args):
         "advection_reaction_3D": ar3d,
         "gram_schmidt": gs,
         "cvDiurnal_kry": cvd,
+        "cvode_fused": cvf,
         "sweep": sweep,
         "per_op": per_op,
         "legs": legs,
@@ -1212,6 +1231,7 @@ def main():
     ap.add_argument("--ar3d-tf", type=float, default=0.05)
     ap.add_argument("--ar3d-fp-tf", type=float, default=5e-4, help="final time of the fixed-point variant of the leg")
     ap.add_argument("--no-gs", action="store_true", help="skip the Gram-Schmidt leg")
+    ap.add_argument("--no-cvfused", action="store_true", help="skip the CVODE fused-kernel plugin leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the (bounded) length sweep leg")
     ap.add_argument("--sweep", action="store_true", help="full length sweep 2^16 .. 2^30 with CPU columns up to 2^26")
     ap.add_argument("--no-cvdiurnal", action="store_true", help="skip the CVODE cvDiurnal_kry leg")
@@ -1221,7 +1241,7 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     if args.only_suite:
-        args.no_diffusion = args.no_ar3d = args.no_gs = args.no_sweep = args.no_cvdiurnal = True
+        args.no_diffusion = args.no_ar3d = args.no_gs = args.no_sweep = args.no_cvdiurnal = args.no_cvfused = True
     if args.impl == "reference":
         return reference_arm(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -35,3 +35,4 @@ def test_bench_line_contract_small_run():
     assert d["cvDiurnal_kry"]["stdout_identical_to_serial_golden"] is True
     assert set(d["sweep"]["lengths"]) == {"2^16", "2^20", "2^24", "2^28"}
     assert len(json.dumps(d["legs"])) < 1400
+    assert len(d["legs"]["cvode_fused"]) == 7 and all(f > 0 for f, _ in d["legs"]["cvode_fused"].values())

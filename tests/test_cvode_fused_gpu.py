@@ -1,7 +1,7 @@
 """libsundials_cvode_fused_b200.so against the reference's own CPU implementation of the same plugin
 boundary (SURVEY §8 row f-N3, include/cvode_fused_b200.h).
 
-Oracle: oracle/_ref/lib/libsundials_cvode_fused_stubs.so = src/cvode/cvode_fused_stubs.c, unmodified,
+Oracle: baseline/_ref/lib/libsundials_cvode_fused_stubs.so = src/cvode/cvode_fused_stubs.c, unmodified,
 running on nvector_serial.  Each of the seven functions is called on both sides with the same seeded
 inputs; every vector the function may write is compared BIT FOR BIT, and so is the return value
 (including the atolmin0 failure of the error-weight functions, after which the weights must be
@@ -17,7 +17,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = Path(__file__).resolve().parent.parent
-STUBS = ROOT / "oracle" / "_ref" / "lib" / "libsundials_cvode_fused_stubs.so"
+STUBS = ROOT / "baseline" / "_ref" / "lib" / "libsundials_cvode_fused_stubs.so"
 FUSED = ROOT / "sundials_b200" / "lib" / "libsundials_cvode_fused_b200.so"
 
 V, D, I = C.c_void_p, C.c_double, C.c_int
@@ -46,7 +46,7 @@ def sides():
     from sundials_b200.plugin import B200Plugin
 
     ref = RefSerial()  # loads libsundials_ref.so + the host framework (RTLD_GLOBAL)
-    assert STUBS.exists(), f"{STUBS} missing: make -C oracle ref"
+    assert STUBS.exists(), f"{STUBS} missing: make -C baseline"
     assert FUSED.exists(), f"{FUSED} missing: python -m sundials_b200.build"
     P = B200Plugin()
     return ref, _bind(C.CDLL(str(STUBS))), P, _bind(C.CDLL(str(FUSED)))

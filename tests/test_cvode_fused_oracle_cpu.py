@@ -1,6 +1,6 @@
 """Pins oracle/cvfused_oracle.py (the formulas the CUDA functors of b200vec_cvfused.cu are written from)
 against the reference's own CPU implementation of CVODE's fused-kernel plugin, src/cvode/cvode_fused_stubs.c
-on nvector_serial (oracle/_ref/lib/libsundials_cvode_fused_stubs.so), bit for bit, over the scalar
+on nvector_serial (baseline/_ref/lib/libsundials_cvode_fused_stubs.so), bit for bit, over the scalar
 branches of N_VLinearSum the op sequences can reach.  Also: the plugin library exports every symbol
 include/cvode_fused_b200.h declares.  No GPU."""
 import ctypes as C
@@ -15,7 +15,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "oracle"))
 import cvfused_oracle as orc  # noqa: E402
 
-STUBS = ROOT / "oracle" / "_ref" / "lib" / "libsundials_cvode_fused_stubs.so"
+STUBS = ROOT / "baseline" / "_ref" / "lib" / "libsundials_cvode_fused_stubs.so"
 V, D, I = C.c_void_p, C.c_double, C.c_int
 N = 2053
 
@@ -23,7 +23,7 @@ N = 2053
 @pytest.fixture(scope="module")
 def stubs(refserial):
     if not STUBS.exists():
-        pytest.skip("oracle/_ref not built (needs /root/reference)")
+        pytest.skip("baseline/_ref not built (needs /root/reference)")
     from test_cvode_fused_gpu import _bind
 
     return refserial, _bind(C.CDLL(str(STUBS)))

@@ -21,10 +21,27 @@ import torch
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tests"))
 import bench  # noqa: E402
 from sundials_b200.plugin import B200Plugin  # noqa: E402
-from test_cvode_fused_gpu import FUSED, STUBS, _bind  # noqa: E402
+
+STUBS = ROOT / "baseline" / "_ref" / "lib" / "libsundials_cvode_fused_stubs.so"
+FUSED = ROOT / "sundials_b200" / "lib" / "libsundials_cvode_fused_b200.so"
+_V, _D, _I = C.c_void_p, C.c_double, C.c_int
+SIGS = {  # src/cvode/cvode_impl.h:639-672
+    "cvEwtSetSS_fused": [_I, _D, _D, _V, _V, _V],
+    "cvEwtSetSV_fused": [_I, _D, _V, _V, _V, _V],
+    "cvCheckConstraints_fused": [_V, _V, _V, _V, _V],
+    "cvNlsResid_fused": [_D, _D, _V, _V, _V, _V],
+    "cvDiagSetup_formY": [_D, _D, _V, _V, _V, _V, _V],
+    "cvDiagSetup_buildM": [_D, _D, _D, _V, _V, _V, _V, _V, _V, _V],
+    "cvDiagSolve_updateM": [_D, _V],
+}
+
+def _bind(lib):
+    for name, args in SIGS.items():
+        f = getattr(lib, name)
+        f.restype, f.argtypes = C.c_int, args
+    return lib
 
 UR = float(np.finfo(np.float64).eps)
 # name -> (vectors, arrays moved per element by the fused kernel, arrays moved by the op sequence, call)
@@ -51,21 +68,17 @@ def timed(fn, reps, stream):
     return e0.elapsed_time(e1) / reps * 1e3  # us
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--log2n", type=int, default=24)
-    ap.add_argument("--reps", type=int, default=20)
-    ap.add_argument("--no-refcuda", action="store_true")
-    a = ap.parse_args()
+def run(log2n=24, reps=20, with_ref_cuda=True):
+    """with_ref_cuda=False touches nothing under oracle/ (bench.py's leg): the unfused arm is the reference's
+    stubs library from baseline/_ref driving NVECTOR_B200"""
+    a = argparse.Namespace(log2n=log2n, reps=reps, no_refcuda=not with_ref_cuda)
     n = 1 << a.log2n
-    torch.cuda.set_device(0)
-    torch.cuda.init()
     pk = ROOT / "MEASURED_PEAKS.json"
     peaks = json.loads(pk.read_text()) if pk.exists() else {}
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
-    core = bench.load_reference()  # host framework + nvector_serial/openmp (RTLD_GLOBAL)
+    core = bench.load_reference() if with_ref_cuda else bench.load_host()  # the host framework (RTLD_GLOBAL)
     stubs, fused = _bind(C.CDLL(str(STUBS))), _bind(C.CDLL(str(FUSED)))
     P = B200Plugin()
     rng = np.random.default_rng(7)
@@ -120,7 +133,18 @@ def main():
             f["speedup_vs_ref_cuda_fused"] = round(t_r / f["fused_us"], 2)
         for v in vc:
             core.N_VDestroy(v)
-    print(json.dumps(out, indent=1))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--log2n", type=int, default=24)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--no-refcuda", action="store_true")
+    a = ap.parse_args()
+    torch.cuda.set_device(0)
+    torch.cuda.init()
+    print(json.dumps(run(a.log2n, a.reps, not a.no_refcuda), indent=1))
 
 
 if __name__ == "__main__":
