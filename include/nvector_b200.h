@@ -30,6 +30,7 @@
 #define NVECTOR_B200_H
 
 #include <stdio.h>
+#include <sundials/sundials_memory.h>
 #include <sundials/sundials_nvector.h>
 
 #include "b200vec.h"
@@ -53,6 +54,11 @@ struct _N_VectorContent_B200
   sunrealtype* host_data;     /* host mirror (DEVICE kind) or the single array       */
   sunrealtype* device_data;   /* device address of the data                          */
   b200vec_ctx ctx;            /* shared execution context (retained)                 */
+  /* vectors created by N_VNewWithMemHelp_B200: the arrays come from the user's allocator */
+  SUNMemoryHelper mem_helper; /* NULL: the context's allocation cache                 */
+  sunbooleantype own_helper;  /* clones own a clone of the helper (cuda:662-663)       */
+  SUNMemory helper_host;      /* what mem_helper handed out for host_data / device_data */
+  SUNMemory helper_device;
 };
 typedef struct _N_VectorContent_B200* N_VectorContent_B200;
 
@@ -63,6 +69,11 @@ N_Vector N_VNewManaged_B200(sunindextype length, SUNContext sunctx);
 N_Vector N_VNewPinned_B200(sunindextype length, SUNContext sunctx);
 /* explicit execution context (stream / workspace / communicator) and memory kind */
 N_Vector N_VNewWithCtx_B200(sunindextype length, int mem_kind, b200vec_ctx ctx, SUNContext sunctx);
+/* host and device arrays (or ONE SUNMEMTYPE_UVM array) allocated and freed through the caller's SUNMemoryHelper,
+   for this vector and -- through a clone of the helper -- for its clones: N_VNewWithMemHelp_Cuda,
+   nvector_cuda.cu:271-310, AllocateData :2226-2270.  Only helper->ops->alloc / dealloc / clone / destroy are used. */
+N_Vector N_VNewWithMemHelp_B200(sunindextype length, sunbooleantype use_managed_mem, SUNMemoryHelper helper,
+                                SUNContext sunctx);
 N_Vector N_VMake_B200(sunindextype length, sunrealtype* h_vdata, sunrealtype* d_vdata, SUNContext sunctx);
 /* wraps ONE user array that both sides can address (cudaMallocManaged / pinned-mapped memory), not
    owned: N_VMakeManaged_Cuda, nvector_cuda.cu:387 */

@@ -196,9 +196,12 @@ int b200vec_ctx_set_stream(b200vec_ctx ctx, void* stream)
 {
   B200_CHECK_CTX(ctx);
   DeviceGuard g(ctx->device);
-  /* pending work on the old stream must finish before results on the new one
-     can depend on it */
-  int rc = check_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  if (ctx->stream == (cudaStream_t)stream) return B200VEC_OK;
+  /* pending work on the old stream must finish before results on the new one can depend on it.  The old
+     handle itself is not touched: its owner may have destroyed it already (the reference's own unit-test
+     driver destroys its stream and then re-policies fresh vectors, test_nvector_cuda.cu:94,158,394), and
+     passing a destroyed stream to the runtime is undefined.  Waiting for the whole device covers it. */
+  int rc      = check_cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
   ctx->stream = (cudaStream_t)stream;
   return rc;
 }

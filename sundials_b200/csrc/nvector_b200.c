@@ -185,11 +185,69 @@ static N_Vector new_shell(SUNContext sunctx, b200vec_ctx ctx)
   return v;
 }
 
+/* the user's allocator (N_VNewWithMemHelp_B200): through the helper's ops table, so that no symbol of
+   sundials_core is needed (SUNMemoryHelper_Alloc is ops->alloc plus argument checks, sundials_memory.c:137) */
+static int helper_alloc_data(N_VectorContent_B200 c, size_t bytes)
+{
+  SUNMemoryHelper h = c->mem_helper;
+  if (c->mem_kind == B200_MEM_MANAGED)
+  {
+    if (h->ops->alloc(h, &c->helper_device, bytes, SUNMEMTYPE_UVM, h->queue) || !c->helper_device) return B200VEC_ERR_NOMEM;
+    c->device_data = c->host_data = (sunrealtype*)c->helper_device->ptr;
+    return B200VEC_OK;
+  }
+  if (h->ops->alloc(h, &c->helper_host, bytes, SUNMEMTYPE_HOST, h->queue) || !c->helper_host) return B200VEC_ERR_NOMEM;
+  if (h->ops->alloc(h, &c->helper_device, bytes, SUNMEMTYPE_DEVICE, h->queue) || !c->helper_device) return B200VEC_ERR_NOMEM;
+  c->host_data   = (sunrealtype*)c->helper_host->ptr;
+  c->device_data = (sunrealtype*)c->helper_device->ptr;
+  return B200VEC_OK;
+}
+
+/* SUNMemoryHelper_Clone (sundials_memory.c:235-253) without sundials_core: the helper's own clone op, or --
+   for a helper without content -- a copy of the object and of its ops table */
+static SUNMemoryHelper helper_clone(SUNMemoryHelper h)
+{
+  if (h->ops->clone) return h->ops->clone(h);
+  if (h->content) return NULL;
+  SUNMemoryHelper k = (SUNMemoryHelper)malloc(sizeof *k);
+  if (!k) return NULL;
+  *k     = *h;
+  k->ops = (SUNMemoryHelper_Ops)malloc(sizeof *(k->ops));
+  if (!k->ops)
+  {
+    free(k);
+    return NULL;
+  }
+  *(k->ops) = *(h->ops);
+  return k;
+}
+
+static void helper_release(N_VectorContent_B200 c)
+{
+  SUNMemoryHelper h = c->mem_helper;
+  if (!h) return;
+  if (c->helper_device) h->ops->dealloc(h, c->helper_device, h->queue);
+  if (c->helper_host) h->ops->dealloc(h, c->helper_host, h->queue);
+  c->helper_device = c->helper_host = NULL;
+  if (c->own_helper)
+  {
+    if (h->ops->destroy) h->ops->destroy(h);
+    else
+    {
+      free(h->ops);
+      free(h);
+    }
+  }
+  c->mem_helper = NULL;
+  c->own_helper = SUNFALSE;
+}
+
 static int alloc_data(N_Vector v)
 {
   N_VectorContent_B200 c = NVC(v);
   size_t bytes           = (size_t)c->length * sizeof(sunrealtype);
   if (c->length == 0) return B200VEC_OK;
+  if (c->mem_helper) return helper_alloc_data(c, bytes);
   int rc;
   void* p = NULL;
   switch (c->mem_kind)
@@ -220,6 +278,14 @@ static int alloc_data(N_Vector v)
 static void free_data(N_Vector v)
 {
   N_VectorContent_B200 c = NVC(v);
+  if (c->helper_device || c->helper_host)
+  { /* arrays from the user's allocator go back to it (the helper itself is released by N_VDestroy_B200) */
+    SUNMemoryHelper h = c->mem_helper;
+    if (c->helper_device) h->ops->dealloc(h, c->helper_device, h->queue);
+    if (c->helper_host) h->ops->dealloc(h, c->helper_host, h->queue);
+    c->helper_device = c->helper_host = NULL;
+    c->device_data = c->host_data = NULL;
+  }
   if (c->own_device && c->device_data)
   {
     size_t bytes = (size_t)c->length * sizeof(sunrealtype);
@@ -253,6 +319,26 @@ N_Vector N_VNewWithCtx_B200(sunindextype length, int mem_kind, b200vec_ctx ctx, 
   {
     fprintf(stderr, "[nvector_b200] allocation of %lld elements failed: %s\n", (long long)length,
             b200vec_last_error());
+    N_VDestroy_B200(v);
+    return NULL;
+  }
+  return v;
+}
+
+N_Vector N_VNewWithMemHelp_B200(sunindextype length, sunbooleantype use_managed_mem, SUNMemoryHelper helper,
+                                SUNContext sunctx)
+{
+  if (sunctx == NULL || length < 0) return NULL;
+  /* cuda:277-288: a helper with the required ops (SUNMemoryHelper_ImplementsRequiredOps, sundials_memory.c:266) */
+  if (!helper || !helper->ops || !helper->ops->alloc || !helper->ops->dealloc || !helper->ops->copy) return NULL;
+  N_Vector v = new_shell(sunctx, NULL);
+  if (!v) return NULL;
+  NVC(v)->length = NVC(v)->global_length = length;
+  NVC(v)->mem_kind                       = use_managed_mem ? B200_MEM_MANAGED : B200_MEM_DEVICE;
+  NVC(v)->mem_helper                     = helper; /* not owned (cuda:298) */
+  if (alloc_data(v) != B200VEC_OK)
+  {
+    fprintf(stderr, "[nvector_b200] the memory helper could not allocate %lld elements\n", (long long)length);
     N_VDestroy_B200(v);
     return NULL;
   }
@@ -360,8 +446,9 @@ sunrealtype* N_VGetHostArrayPointer_B200(N_Vector v)
   N_VectorContent_B200 c = NVC(v);
   if (c->mem_kind == B200_MEM_DEVICE)
   {
-    if (!c->host_data && c->length > 0)
-    { /* lazily created pinned mirror (the reference allocates it eagerly, cuda:2226) */
+    if (!c->host_data && c->device_data && c->length > 0)
+    { /* lazily created pinned mirror (the reference allocates it eagerly, cuda:2226); an empty clone
+         (no device array yet) has no host side either, as Test_N_VCloneEmpty's has_data expects */
       void* p = NULL;
       CHECK_ON(v, b200vec_malloc_host(c->ctx, (size_t)c->length * sizeof(sunrealtype), &p));
       c->host_data = (sunrealtype*)p;
@@ -479,6 +566,20 @@ N_Vector N_VCloneEmpty_B200(N_Vector w)
   c->host_data   = NULL;
   c->device_data = NULL;
   c->own_device = c->own_host = SUNFALSE;
+  c->helper_host = c->helper_device = NULL;
+  c->own_helper                     = SUNFALSE;
+  if (c->mem_helper)
+  { /* cuda:662-663: every clone owns a clone of the helper */
+    c->mem_helper = helper_clone(c->mem_helper);
+    if (!c->mem_helper)
+    {
+      free(c);
+      free(v->ops);
+      free(v);
+      return NULL;
+    }
+    c->own_helper = SUNTRUE;
+  }
   b200vec_ctx_retain(c->ctx);
   v->content = c;
   return v;
@@ -503,6 +604,7 @@ void N_VDestroy_B200(N_Vector v)
   if (v->content != NULL)
   {
     free_data(v);
+    helper_release(NVC(v));
     b200vec_ctx_release(NCTX(v));
     free(v->content);
     v->content = NULL;

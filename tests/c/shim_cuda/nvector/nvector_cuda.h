@@ -26,6 +26,7 @@ static inline N_Vector b200_shim_as_cuda(N_Vector v)
 #define N_VNewEmpty_Cuda(ctx)            b200_shim_as_cuda(N_VNewEmpty_B200(ctx))
 #define N_VMake_Cuda(n, h, d, ctx)       b200_shim_as_cuda(N_VMake_B200(n, h, d, ctx))
 #define N_VMakeManaged_Cuda(n, p, ctx)   b200_shim_as_cuda(N_VMakeManaged_B200(n, p, ctx))
+#define N_VNewWithMemHelp_Cuda(n, managed, helper, ctx) b200_shim_as_cuda(N_VNewWithMemHelp_B200(n, managed, helper, ctx))
 #define N_VClone_Cuda                 N_VClone_B200
 #define N_VCloneEmpty_Cuda            N_VCloneEmpty_B200
 #define N_VDestroy_Cuda               N_VDestroy_B200

@@ -53,6 +53,22 @@ def test_reference_nvector_unit_harness_tiny_lengths():
         assert r.returncode == 0 and "SUCCESS" in r.stdout, r.stdout[-2000:]
 
 
+@pytest.mark.parametrize("args", [(3, 32, 0), (500, 128, 0), (1000, 0, 0)])
+def test_reference_cuda_unit_test_driver_unmodified(args):
+    """test/unit_tests/nvector/cuda/test_nvector_cuda.cu -- the reference's OWN driver for nvector_cuda, compiled
+    unmodified against the shim header (N_V*_Cuda -> N_V*_B200), with the reference's CTest arguments
+    (cuda/CMakeLists.txt:24-26: length, threads per block, timing).  It runs every op's known-answer test for 4
+    execution-policy variants (default, a user stream that it destroys afterwards, grid-stride, block reductions)
+    x 3 memory variants (device + host mirror, managed, a user-supplied SUNMemoryHelper ->
+    N_VNewWithMemHelp_B200), fused ops off and on, and expects N_VGetVectorID == SUNDIALS_NVEC_CUDA."""
+    r = _run("test_nvector_cuda_b200", *args)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert r.stdout.count("SUCCESS: NVector module passed all tests") == 4, r.stdout[-2000:]
+    assert "FAIL" not in r.stdout
+    assert r.stdout.count("Testing CUDA N_Vector with SUNMemoryHelper") == 4
+    assert r.stdout.count("PASSED test -- N_VGetVectorID") == 12
+
+
 def test_gram_schmidt_bit_identical_small():
     r = _run("test_gs_b200", 1000, 10, 0)
     assert r.returncode == 0, r.stdout
