@@ -71,4 +71,33 @@ static inline void N_VCopyFromDevice_Cuda(N_Vector) {}
 static inline sunbooleantype N_VIsManagedMemory_Cuda(N_Vector) { return SUNTRUE; }
 #define N_VEnableFusedOps_Cuda N_VEnableFusedOps_Serial
 
+/* execution policies mean nothing to a CPU vector: accepted and ignored (the oracle runs are made with
+   CUDA_LAUNCH_BLOCKING=1, so that the example's kernels have finished when the host code reads the arrays) */
+class SUNCudaExecPolicy
+{
+public:
+  virtual ~SUNCudaExecPolicy() {}
+};
+class SUNCudaThreadDirectExecPolicy : public SUNCudaExecPolicy
+{
+public:
+  SUNCudaThreadDirectExecPolicy(int, cudaStream_t = 0) {}
+};
+class SUNCudaGridStrideExecPolicy : public SUNCudaExecPolicy
+{
+public:
+  SUNCudaGridStrideExecPolicy(int, int, cudaStream_t = 0) {}
+};
+class SUNCudaBlockReduceExecPolicy : public SUNCudaExecPolicy
+{
+public:
+  SUNCudaBlockReduceExecPolicy(int, int = 0, cudaStream_t = 0) {}
+};
+class SUNCudaBlockReduceAtomicExecPolicy : public SUNCudaExecPolicy
+{
+public:
+  SUNCudaBlockReduceAtomicExecPolicy(int, int = 0, cudaStream_t = 0) {}
+};
+static inline SUNErrCode N_VSetKernelExecPolicy_Cuda(N_Vector, SUNCudaExecPolicy*, SUNCudaExecPolicy*) { return SUN_SUCCESS; }
+
 #endif

@@ -6,7 +6,9 @@ running on NVECTOR_B200 through the N_Vector_Ops table (tests/c/Makefile):
   * SUNModifiedGS / SUNClassicalGS (sundials_iterative.c) serial vs B200;
   * SPGMR / SPFGMR / PCG unit tests (1e-13 solves, both Gram-Schmidt types);
   * CVODE cvDiurnal_kry, ARKODE ark_heat1D + ark_heat2D, IDA idaHeat2D_kry,
-    KINSOL kinFoodWeb_kry + kinLaplace_picard_kry.
+    KINSOL kinFoodWeb_kry + kinLaplace_picard_kry;
+  * the reference's CUDA programs through tests/c/shim_cuda (N_V*_Cuda -> N_V*_B200): its own nvector_cuda unit-test
+    driver, cvAdvDiff_kry_cuda[_managed], cvAdvDiff_diag_cuda (integrator fused kernels), idaHeat2D_kry_cuda.
 
 The integrator programs must print output BYTE-IDENTICAL to the goldens that the
 same sources produced on the reference's nvector_serial
@@ -134,6 +136,36 @@ def test_reference_cuda_example_with_device_rhs_kernels():
     strip = lambda t: re.sub(r"(leniw(LS)?\s*=\s*)\d+", r"\1#", t)  # noqa: E731
     assert strip(r.stdout) == strip(want), _first_diff(strip(r.stdout), strip(want))
     assert "nst     =   143" in r.stdout and "nli     =   225" in r.stdout
+
+
+@pytest.mark.parametrize("prog", ["cvAdvDiff_kry_cuda_managed", "idaHeat2D_kry_cuda"])
+def test_more_reference_cuda_examples_unmodified(prog):
+    """examples/cvode/cuda/cvAdvDiff_kry_cuda_managed.cu (managed memory, non-default execution policies) and
+    examples/ida/cuda/idaHeat2D_kry_cuda.cu (IDA + SPGMR with device residual / preconditioner kernels), UNMODIFIED
+    through the shim header: stdout equals the output the reference ships for them on nvector_cuda (integer
+    workspace sizes aside: N_VSpace reports liw = 1 like nvector_serial, nvector_cuda 2)."""
+    import re
+
+    r = _run(prog + "_b200")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    want = (GOLD / f"{prog}.refcuda.out").read_text()
+    strip = lambda t: re.sub(r"(leniw(LS)?\s*=\s*)\d+", r"\1#", t)  # noqa: E731
+    assert strip(r.stdout) == strip(want), _first_diff(strip(r.stdout), strip(want))
+
+
+@pytest.mark.parametrize("prog", ["cvAdvDiff_kry_cuda", "cvAdvDiff_kry_cuda_managed", "idaHeat2D_kry_cuda"])
+def test_reference_cuda_examples_identical_to_the_reference_cpu_vector(prog):
+    """the ORACLE build of the same unmodified source (tests/c/shim_serial_managed: the reference's nvector_serial over
+    managed memory, only the example's own kernels on the GPU; CUDA_LAUNCH_BLOCKING=1 so that they have finished
+    when the host code reads) run side by side: byte-identical stdout, leniw included"""
+    import os
+
+    got = _run(prog + "_b200")
+    ref = subprocess.run([str(BIN / (prog + "_serial"))], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, CUDA_LAUNCH_BLOCKING="1"))
+    assert got.returncode == 0 and ref.returncode == 0, got.stderr[-1500:] + ref.stderr[-1500:]
+    assert got.stdout == ref.stdout, _first_diff(got.stdout, ref.stdout)
+    assert len(got.stdout) > 500
 
 
 def _diag(toltype, fused):
