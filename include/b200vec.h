@@ -63,6 +63,9 @@ int b200vec_ctx_retain(b200vec_ctx ctx);
 int b200vec_ctx_release(b200vec_ctx ctx); /* destroys when the last reference goes */
 /* process-wide default context on the current device / legacy stream */
 int b200vec_ctx_default(b200vec_ctx* out);
+/* all later work of the context goes to `stream`; waits for the DEVICE first (not for the previous stream,
+ * whose handle the caller may already have destroyed).  The caller keeps the stream alive while the context
+ * uses it -- the lifetime rule of the reference's execution-policy objects (sundials_cuda_policies.hpp:71-90). */
 int b200vec_ctx_set_stream(b200vec_ctx ctx, void* stream);
 void* b200vec_ctx_get_stream(b200vec_ctx ctx);
 int b200vec_ctx_device(b200vec_ctx ctx);
